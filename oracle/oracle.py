@@ -1,0 +1,75 @@
+"""ctypes wrapper of the CPU oracle.  TEST INFRASTRUCTURE ONLY (see boundmpc_oracle.cpp)."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libboundmpc_oracle.so")
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("boundmpc_oracle.cpp", "ocp_model.hpp", "ad.hpp")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def dims(N=10, S=4):
+    n, m, np_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib().orc_dims(N, S, ctypes.byref(n), ctypes.byref(m), ctypes.byref(np_))
+    return n.value, m.value, np_.value
+
+
+def bounds(N=10, S=4, dt=0.1):
+    n, m, _ = dims(N, S)
+    lbx, ubx, lbg, ubg = np.empty(n), np.empty(n), np.empty(m), np.empty(m)
+    lib().orc_bounds(N, S, ctypes.c_double(dt), _p(lbx), _p(ubx), _p(lbg), _p(ubg))
+    return lbx, ubx, lbg, ubg
+
+
+def eval_fg(x, p, N=10, S=4, dt=0.1):
+    n, m, _ = dims(N, S)
+    x = np.ascontiguousarray(x, float)
+    p = np.ascontiguousarray(p, float)
+    f = ctypes.c_double()
+    g = np.empty(m)
+    lib().orc_eval(N, S, ctypes.c_double(dt), _p(x), _p(p), ctypes.byref(f), _p(g))
+    return f.value, g
+
+
+def derivs(x, p, lam, N=10, S=4, dt=0.1):
+    n, m, _ = dims(N, S)
+    x = np.ascontiguousarray(x, float)
+    p = np.ascontiguousarray(p, float)
+    lam = np.ascontiguousarray(lam, float)
+    grad, jac, hess = np.empty(n), np.empty((m, n)), np.empty((n, n))
+    lib().orc_derivs(N, S, ctypes.c_double(dt), _p(x), _p(p), _p(lam), _p(grad), _p(jac), _p(hess))
+    return grad, jac, hess
+
+
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=0.1, bound_push=1e-3, verbose=0):
+    n, m, _ = dims(N, S)
+    x0 = np.ascontiguousarray(x0, float)
+    p = np.ascontiguousarray(p, float)
+    opts = np.array([tol, max_iter, mu_init, bound_push, verbose], float)
+    x, g, lam_g, lam_x = np.empty(n), np.empty(m), np.empty(m), np.empty(n)
+    f, it, kkt = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
+    st = lib().orc_solve(N, S, ctypes.c_double(dt), _p(x0), _p(p), _p(opts), _p(x), _p(g), _p(lam_g), _p(lam_x),
+                         ctypes.byref(f), ctypes.byref(it), ctypes.byref(kkt))
+    return dict(x=x, g=g, lam_g=lam_g, lam_x=lam_x, f=f.value, iters=it.value, kkt=kkt.value, status=st)

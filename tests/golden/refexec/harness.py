@@ -172,8 +172,11 @@ def make_reference_mpc(scn, backend, n=10, real_time=True):
     s = copy.deepcopy(scn)
     params = _Params(n=n, nr_segs=s['nr_segs'], dt=s['dt'], weights=s['weights'],
                      real_time=real_time)
-    mpc = BoundMPC(s['p_via'], s['r_via'], [s['p_upper'], s['p_lower']],
-                   [s['r_upper'], s['r_lower']], s['bp1'], s['br1'], s['s'],
+    # The runner -> create_traj_msg -> node chain swaps upper/lower twice
+    # (util_functions.py:58-70, bound_mpc_node.py:57-58, ReferencePath.py:52-55); the net effect
+    # is pos_lim = [lower, upper] as ReferencePath reads it.
+    mpc = BoundMPC(s['p_via'], s['r_via'], [s['p_lower'], s['p_upper']],
+                   [s['r_lower'], s['r_upper']], s['bp1'], s['br1'], s['s'],
                    s['e_p_min'], s['e_r_min'], s['e_p_max'], s['e_r_max'],
                    p0=np.array(s['p0fk']), params=params)
     return mpc
