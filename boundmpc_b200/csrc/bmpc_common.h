@@ -1,0 +1,168 @@
+// boundmpc_b200 — shared definitions of the CUDA solver.
+//
+// Execution model: one CTA solves one OCP instance ("instance" = one call of the
+// reference's `self.solver(x0, lbx, ubx, lbg, ubg, p)`, BoundMPC.py:446-453).  The code is
+// written as a sequence of *parallel phases*: `PAR_FOR(i, n)` distributes the items of a
+// phase over the threads of the CTA, `BMPC_SYNC()` separates phases, and block-wide
+// reductions hand their result to every thread so that control flow stays CTA-uniform.
+// With BMPC_HOST_EMU defined the same source compiles for the host with a single
+// "thread" (tid 0 of 1); tests/emu uses that build to check the kernel source on CPU
+// machines.  The product library never contains the host build.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef BMPC_HOST_EMU
+#define BMPC_DEV inline
+#define BMPC_SYNC() ((void)0)
+#define BMPC_LDG(ptr) (*(ptr))
+#else
+#define BMPC_DEV __device__ __forceinline__
+#define BMPC_SYNC() __syncthreads()
+#define BMPC_LDG(ptr) __ldg(ptr)
+#endif
+
+#define PAR_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nt)
+
+namespace bmpc {
+
+struct Ctx {
+  int tid, nt;
+  double* red;  // shared scratch for block reductions (>= 40 doubles)
+};
+
+// ---- stage layout (casadi_ocp_formulation.py:90-153) ----------------------
+constexpr int NX = 44;   // variables per stage: [u(7) u_phi q(7) dq(7) ddq(7) p_pos(3) p_rot(3) v_lin(3) v_ang(3) phi dphi ddphi]
+constexpr int NU = 8;
+constexpr int NE = 36;   // equality rows per stage (casadi_ocp_formulation.py:271-303)
+constexpr int NQ = 7;    // inequality rows per stage in the reference's form (casadi_ocp_formulation.py:305-349)
+constexpr int NG = 43;   // rows of g per stage
+constexpr int ND = 12;   // inequality rows in interval form (see DESIGN.md "interval form")
+constexpr int NZ = 52;   // (s_k, u_k): previous stage block + current input
+enum { oU = 0, oUPHI = 7, oQ = 8, oDQ = 15, oDDQ = 22, oPPOS = 29, oPROT = 32, oVLIN = 35,
+       oVANG = 38, oPHI = 41, oDPHI = 42, oDDPHI = 43 };
+// rows of the x-part (stage offset minus 8); the 12 kinematic rows are contiguous
+constexpr int rKIN = 21;  // p_pos(3) p_rot(3) v_lin(3) v_ang(3)
+constexpr int NK = 12;
+
+// ---- parameter vector layout for nr_segs = S (casadi_ocp_formulation.py:361-376, App. A.3)
+struct PLayout {
+  int S, np;
+  int q0, dq0, ddq0, phi0, p0, v0, iwref, dtau, par, orth1, orth2, xphid, jerk, phisw, jacr, jacl;
+  int pref, dpref, dpn, bp1, bp2, br1, br2, a4, a3, a2, a1, a0, w, phimax, dphimax, v1, v2, v3, qd;
+};
+BMPC_DEV PLayout make_layout(int S) {
+  PLayout L;
+  L.S = S;
+  L.q0 = 0; L.dq0 = 7; L.ddq0 = 14; L.phi0 = 21; L.p0 = 24; L.v0 = 30; L.iwref = 36; L.dtau = 39; L.par = 42;
+  L.orth1 = 42 + 3 * S; L.orth2 = 42 + 6 * S; L.xphid = 42 + 9 * S; L.jerk = 45 + 9 * S;
+  L.phisw = 53 + 9 * S; L.jacr = 54 + 10 * S; L.jacl = 63 + 10 * S; L.pref = 72 + 10 * S;
+  L.dpref = 72 + 16 * S; L.dpn = 72 + 22 * S; L.bp1 = 72 + 25 * S; L.bp2 = 72 + 28 * S;
+  L.br1 = 72 + 31 * S; L.br2 = 72 + 34 * S; L.a4 = 72 + 37 * S; L.a3 = 81 + 46 * S;
+  L.a2 = 90 + 55 * S; L.a1 = 99 + 64 * S; L.a0 = 108 + 73 * S; L.w = 117 + 82 * S;
+  L.phimax = 132 + 82 * S; L.dphimax = 133 + 82 * S; L.v1 = 134 + 82 * S; L.v2 = 134 + 85 * S;
+  L.v3 = 134 + 88 * S; L.qd = 134 + 91 * S; L.np = 141 + 91 * S;
+  return L;
+}
+
+// ---- problem description shared by all instances of a handle -------------------------------
+struct Config {
+  int N, S, n, m, np;
+  double dt;
+  double lb[NX], ub[NX];   // per-stage variable bounds (+-inf where free)
+  // interior-point options
+  double tol;
+  int max_iter;
+  double mu_init, bound_push;
+  double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
+  double gamma_theta, gamma_phi, eta_phi, s_phi, s_theta;
+  // integration coefficients of the piecewise-linear jerk at t = h (App. A.4)
+  double a_dq, a_ddq, a_um, a_u, b_ddq, b_um, b_u, c_um, c_u;
+  PLayout L;
+};
+
+// ---- per-stage record produced by the evaluation phases (doubles) --------------------------
+// GK    [12][52]  kinematic rows of [A_hat | B]  (columns: previous stage block (44), u_k (8))
+// HQQn  [7][7]    multiplier-weighted d2 Phi / dq_n dq_n      (integrated state)
+// HQDn  [7][7]    d2 Phi / dq_n d(dq_n)   (row: q, col: dq)
+// HQQk, HQDk      same for the omega(q_k, dq_k) term of the p_rot rows
+// HY    [7][7]    Hessian of the path cost w.r.t. y = (p_pos, p_rot, phi)
+// GY    [7]       gradient of the path cost w.r.t. y
+// JD    [12][8]   gradients of the interval rows: y(7) then dphi
+// HD    [12]      second derivative of each interval row w.r.t. phi
+// DPD   [6]       dp_d of the active segment (velocity / acceleration tracking terms)
+// MISC            see offsets
+enum {
+  R_GK = 0,
+  R_HQQN = R_GK + NK * NZ,
+  R_HQDN = R_HQQN + 49,
+  R_HQQK = R_HQDN + 49,
+  R_HQDK = R_HQQK + 49,
+  R_HY = R_HQDK + 49,
+  R_GY = R_HY + 49,
+  R_JD = R_GY + 7,
+  R_HD = R_JD + ND * 8,
+  R_DPD = R_HD + ND,
+  R_GV = R_DPD + 6,        // [6] gradient w.r.t. v (velocity + acceleration tracking)
+  R_GVP = R_GV + 6,        // [6] gradient w.r.t. v_prev
+  R_GPH = R_GVP + 6,       // [2] gradient w.r.t. dphi, ddphi (tracking + path-state cost); phi part is in GY
+  R_COST = R_GPH + 2,      // [1] stage cost
+  R_SIZE = R_COST + 2
+};
+// forward-kinematics scratch of one chain evaluation
+enum {
+  F_Z = 0,                 // [7][3] joint axes
+  F_R = F_Z + 21,          // [7][3] tool point minus joint origin
+  F_W = F_R + 21,          // [7][3] sum_{k>=i} dq_k z_k x r_k
+  F_OT = F_W + 21,         // [7][3] sum_{k>i} dq_k z_k
+  F_OH = F_OT + 21,        // [8][3] sum_{k<i} dq_k z_k   (entry 7 = total angular velocity)
+  F_POS = F_OH + 24,       // [3]
+  F_Q = F_POS + 3,         // [7] joint angles of this evaluation
+  F_DQ = F_Q + 7,          // [7]
+  F_SIZE = F_DQ + 8
+};
+
+BMPC_DEV void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+BMPC_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ---- block reductions: result is returned to every thread ------------------------------------
+enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+template <int K>
+BMPC_DEV void block_reduce(const Ctx& cx, double (&v)[K], const int (&op)[K]) {
+#ifndef BMPC_HOST_EMU
+  const int lane = cx.tid & 31, warp = cx.tid >> 5, nw = (cx.nt + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double a = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double b = __shfl_xor_sync(0xffffffffu, a, o);
+      a = op[k] == RED_SUM ? a + b : (op[k] == RED_MAX ? fmax(a, b) : fmin(a, b));
+    }
+    if (lane == 0) cx.red[k * 32 + warp] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double a = cx.red[k * 32];
+    for (int w = 1; w < nw; w++) {
+      double b = cx.red[k * 32 + w];
+      a = op[k] == RED_SUM ? a + b : (op[k] == RED_MAX ? fmax(a, b) : fmin(a, b));
+    }
+    v[k] = a;
+  }
+  __syncthreads();
+#else
+  (void)cx; (void)v; (void)op;
+#endif
+}
+
+// status codes returned per instance
+enum { ST_SUCCESS = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_NUMERIC = 4 };
+
+}  // namespace bmpc

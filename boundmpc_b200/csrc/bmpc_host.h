@@ -1,0 +1,43 @@
+// boundmpc_b200 — host-side construction of the solver configuration from the C-ABI struct.
+#pragma once
+#include <math.h>
+#include "../../include/boundmpc_b200.h"
+#include "bmpc_common.h"
+
+namespace bmpc {
+
+// variable bounds and options exactly as setup_optimization_problem receives / builds them
+// (casadi_ocp_formulation.py:92-153) and the Ipopt options of BoundMPC.py:120-141
+inline int make_config(const bmpc_config& in, Config& C) {
+  if (in.N < 1 || in.N > 64 || in.nr_segs < 2 || in.nr_segs > 16 || !(in.dt > 0)) return -1;
+  C.N = in.N; C.S = in.nr_segs; C.n = NX * in.N; C.m = NG * in.N; C.dt = in.dt;
+  C.L = make_layout(in.nr_segs);
+  C.np = C.L.np;
+  for (int i = 0; i < NX; i++) { C.lb[i] = -INFINITY; C.ub[i] = INFINITY; }
+  for (int i = 0; i < 7; i++) {
+    C.lb[oU + i] = in.u_min; C.ub[oU + i] = in.u_max;
+    C.lb[oQ + i] = in.q_lim_lower[i]; C.ub[oQ + i] = in.q_lim_upper[i];
+    C.lb[oDQ + i] = in.dq_lim_lower[i]; C.ub[oDQ + i] = in.dq_lim_upper[i];
+  }
+  C.lb[oUPHI] = in.ut_min; C.ub[oUPHI] = in.ut_max;
+  C.lb[oPHI] = 0.0;
+  C.tol = in.tol > 0 ? in.tol : 1e-8;
+  C.max_iter = in.max_iter > 0 ? in.max_iter : 500;
+  C.mu_init = in.mu_init > 0 ? in.mu_init : 0.1;
+  C.bound_push = in.bound_push > 0 ? in.bound_push : 1e-3;
+  C.kappa_eps = 10.0; C.kappa_mu = 0.2; C.theta_mu = 1.5; C.tau_min = 0.99; C.s_max = 100.0;
+  C.gamma_theta = 1e-5; C.gamma_phi = 1e-5; C.eta_phi = 1e-8; C.s_phi = 2.3; C.s_theta = 1.1;
+  const double h = in.dt;
+  C.a_dq = h; C.a_ddq = h * h / 2; C.a_um = h * h * h / 8; C.a_u = h * h * h / 24;
+  C.b_ddq = h; C.b_um = h * h / 3; C.b_u = h * h / 6; C.c_um = h / 2; C.c_u = h / 2;
+  return 0;
+}
+
+inline void fill_bounds(const Config& C, double* lbx, double* ubx, double* lbg, double* ubg) {
+  for (int k = 0; k < C.N; k++) {
+    for (int i = 0; i < NX; i++) { lbx[NX * k + i] = C.lb[i]; ubx[NX * k + i] = C.ub[i]; }
+    for (int i = 0; i < NG; i++) { lbg[NG * k + i] = i < NE ? 0.0 : -INFINITY; ubg[NG * k + i] = 0.0; }
+  }
+}
+
+}  // namespace bmpc

@@ -1,0 +1,287 @@
+// boundmpc_b200 — primal-dual interior-point iteration (kernel family (b1)).
+//
+// Replaces the Ipopt solve behind `self.solver(x0=, lbx=, ubx=, lbg=, ubg=, p=)`
+// (BoundMPC.py:446-457; options BoundMPC.py:120-141).  Same problem
+// statement as Ipopt's: equality rows c(x) = 0, inequality rows with slacks d(x) + s = 0,
+// s >= 0, variable bounds by log barriers with multipliers z_L, z_U; Newton step on the
+// perturbed KKT conditions, fraction-to-the-boundary rule, filter line search, monotone
+// barrier update, inertia correction by Hessian perturbation, Ipopt's scaled termination
+// error.  Like the reference call (BoundMPC.py:451-452 leaves lam_g0 / lam_x0 commented out)
+// every solve starts from zero equality multipliers.
+//
+// Inequality rows 38..42 of the reference are (m)^2 - h^2 <= 0 with h > 0
+// (casadi_ocp_formulation.py:317-349); the iteration works on the equivalent pair
+// m - h <= 0, -m - h <= 0 ("interval form": same feasible set, same KKT points, and the
+// quadratic form's vanishing gradient at m = 0 is avoided).  `g` and `lam_g` are reported in
+// the reference's form: lam = (z_plus + z_minus) / (2 h).
+#pragma once
+#include "bmpc_riccati.cuh"
+
+namespace bmpc {
+
+struct InstanceIO {
+  const double* x0;   // [n]
+  const double* p;    // [np]
+  double* x;          // [n]
+  double* g;          // [m]
+  double* lam_g;      // [m]
+  double* lam_x;      // [n]
+  double* f;          // [1]
+  double* kkt;        // [1]
+  int32_t* iters;     // [1]
+  int32_t* status;    // [1]
+};
+
+BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
+
+BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io) {
+  const int N = C.N, n = C.n, ne = NE * N, nd = ND * N;
+  const double* p = io.p;
+  // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)
+  build_wp0(cx, C, p, W.wp0);
+  PAR_FOR(i, n) {
+    const int ii = i % NX;
+    double v = BMPC_LDG(io.x0 + i);
+    const double l = C.lb[ii], u = C.ub[ii];
+    const bool fl = l > -1e300, fu = u < 1e300;
+    if (fl && fu) {
+      const double pl = fmin(C.bound_push * fmax(1.0, fabs(l)), C.bound_push * (u - l));
+      const double pu = fmin(C.bound_push * fmax(1.0, fabs(u)), C.bound_push * (u - l));
+      v = fmin(fmax(v, l + pl), u - pu);
+    } else if (fl) v = fmax(v, l + C.bound_push * fmax(1.0, fabs(l)));
+    else if (fu) v = fmin(v, u - C.bound_push * fmax(1.0, fabs(u)));
+    W.x[i] = v;
+  }
+  PAR_FOR(i, ne) W.y[i] = 0.0;
+  BMPC_SYNC();
+  double mu = C.mu_init;
+  eval_values(cx, C, W, p, W.x, W.c, W.d);
+  PAR_FOR(i, nd) { const double sv = fmax(-W.d[i], C.bound_push); W.s[i] = sv; W.zs[i] = mu / sv; }
+  PAR_FOR(i, n) {
+    const int ii = i % NX;
+    const double l = C.lb[ii], u = C.ub[ii];
+    W.zL[i] = l > -1e300 ? mu / (W.x[i] - l) : 0.0;
+    W.zU[i] = u < 1e300 ? mu / (u - W.x[i]) : 0.0;
+  }
+  if (cx.tid == 0) S.flag[1] = 0;   // filter size
+  BMPC_SYNC();
+
+  int nbnd = 0;
+  for (int i = 0; i < NX; i++) nbnd += (C.lb[i] > -1e300) + (C.ub[i] < 1e300);
+  const double nzcnt = (double)N * (ND + nbnd);
+  double theta_max = 0.0, theta_min = 0.0, delta_w_last = 0.0, kkt_final = 0.0, fval = 0.0;
+  bool have_theta0 = false;
+  int status = ST_MAXITER, it = 0, ls_fail = 0;
+
+  for (;; it++) {
+    eval_full(cx, C, W, p, W.x);
+    // ---- optimality error (Ipopt's E_mu), constraint violation theta
+    double rv[8] = {0, 0, 0, 0, 1e300, 0, 0, 0};   // dinf, pinf, ysum, zsum, szmin, szmax, theta, f
+    PAR_FOR(i, n) {
+      const int k = i / NX, a = i - NX * k;
+      double r = W.gradf[i] - W.zL[i] + W.zU[i];
+      const double* GKk = W.rec + (size_t)k * R_SIZE + R_GK;
+      if (a < 8) r += GT_vec(C, GKk, W.y + NE * k, NX + a);
+      else r -= W.y[NE * k + a - 8];
+      if (k + 1 < N) r += GT_vec(C, GKk + R_SIZE, W.y + NE * (k + 1), a);
+      const int ya = (a >= oPPOS && a < oPPOS + 6) ? a - oPPOS : (a == oPHI ? 6 : (a == oDPHI ? 7 : -1));
+      if (ya >= 0) {
+        const double* JD = W.rec + (size_t)k * R_SIZE + R_JD;
+        for (int q = 0; q < ND; q++) r += JD[q * 8 + ya] * W.zs[ND * k + q];
+      }
+      rv[0] = fmax(rv[0], fabs(r));
+      const double l = C.lb[a], u = C.ub[a];
+      if (l > -1e300) { const double pr = (W.x[i] - l) * W.zL[i]; rv[3] += W.zL[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
+      if (u < 1e300) { const double pr = (u - W.x[i]) * W.zU[i]; rv[3] += W.zU[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
+    }
+    PAR_FOR(i, ne) { const double cv = fabs(W.c[i]); rv[1] = fmax(rv[1], cv); rv[2] += fabs(W.y[i]); rv[6] += cv; }
+    PAR_FOR(i, nd) {
+      const double dv = fabs(W.d[i] + W.s[i]), pr = W.s[i] * W.zs[i];
+      rv[1] = fmax(rv[1], dv); rv[6] += dv; rv[3] += W.zs[i];
+      rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr);
+    }
+    PAR_FOR(k, N) rv[7] += W.cost[k];
+    {
+      const int ops[8] = {RED_MAX, RED_MAX, RED_SUM, RED_SUM, RED_MIN, RED_MAX, RED_SUM, RED_SUM};
+      block_reduce<8>(cx, rv, ops);
+    }
+    const double dinf = rv[0], pinf = rv[1], ysum = rv[2], zsum = rv[3], szmin = rv[4], szmax = rv[5], th_cur = rv[6];
+    fval = rv[7];
+    const double sd = fmax(C.s_max, (ysum + zsum) / (ne + nzcnt)) / C.s_max;
+    const double sc = fmax(C.s_max, zsum / nzcnt) / C.s_max;
+    const double e0 = fmax(dinf / sd, fmax(pinf, fmax(szmax, 0.0) / sc));
+    kkt_final = e0;
+    if (!(e0 == e0) || !(th_cur < 1e300)) { status = ST_NUMERIC; break; }
+    if (e0 <= C.tol) { status = ST_SUCCESS; break; }
+    if (it >= C.max_iter) { status = ST_MAXITER; break; }
+    // ---- barrier parameter: monotone Fiacco-McCormick (Waechter & Biegler 2006, eq. (7))
+    bool mu_changed = false;
+    for (;;) {
+      const double emu = fmax(dinf / sd, fmax(pinf, fmax(szmax - mu, mu - szmin) / sc));
+      if (!(mu > C.tol / 10 && emu <= C.kappa_eps * mu)) break;
+      mu = fmax(C.tol / 10, fmin(C.kappa_mu * mu, pow(mu, C.theta_mu)));
+      mu_changed = true;
+    }
+    if (mu_changed) { if (cx.tid == 0) S.flag[1] = 0; BMPC_SYNC(); }
+    if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * fmax(1.0, th_cur); theta_min = 1e-4 * fmax(1.0, th_cur); }
+    // ---- search direction with inertia correction
+    double dwreg = 0.0;
+    bool ok = kkt_solve(cx, C, W, p, S, mu, 0.0);
+    if (!ok) {
+      dwreg = delta_w_last == 0.0 ? 1e-4 : fmax(1e-20, delta_w_last / 3);
+      for (int tries = 0; tries < 60; tries++) {
+        ok = kkt_solve(cx, C, W, p, S, mu, dwreg);
+        if (ok) break;
+        dwreg *= (delta_w_last == 0.0 ? 100.0 : 8.0);
+        if (dwreg > 1e40) break;
+      }
+      if (!ok) { status = ST_REGULARIZATION; break; }
+      delta_w_last = dwreg;
+    }
+    // ---- remaining step components, fraction to the boundary, barrier objective and its slope
+    const double tau = fmax(C.tau_min, 1.0 - mu);
+    double sv4[4] = {1.0, 1.0, 0.0, 0.0};   // alpha_pr, alpha_du, dphi, phi_cur(barrier part)
+    PAR_FOR(i, nd) {
+      const int k = i / ND, r = i - ND * k;
+      const double* JD = W.rec + (size_t)k * R_SIZE + R_JD + r * 8;
+      const double* dw = W.dx + NX * k;
+      double jd = JD[6] * dw[oPHI] + JD[7] * dw[oDPHI];
+      for (int q = 0; q < 6; q++) jd += JD[q] * dw[oPPOS + q];
+      const double sv = W.s[i], zv = W.zs[i];
+      const double dsv = -(W.d[i] + sv) - jd;
+      const double dzv = mu / sv - zv - zv / sv * dsv;
+      W.ds[i] = dsv; W.dzs[i] = dzv;
+      if (dsv < 0) sv4[0] = fmin(sv4[0], -tau * sv / dsv);
+      if (dzv < 0) sv4[1] = fmin(sv4[1], -tau * zv / dzv);
+      sv4[2] -= mu * dsv / sv;
+      sv4[3] -= mu * log(sv);
+    }
+    PAR_FOR(i, n) {
+      const int a = i % NX;
+      const double l = C.lb[a], u = C.ub[a], dxi = W.dx[i];
+      double dl = 0.0, du = 0.0;
+      sv4[2] += W.gradf[i] * dxi;
+      if (l > -1e300) {
+        const double sl = W.x[i] - l, z = W.zL[i];
+        dl = mu / sl - z - z / sl * dxi;
+        if (dxi < 0) sv4[0] = fmin(sv4[0], -tau * sl / dxi);
+        if (dl < 0) sv4[1] = fmin(sv4[1], -tau * z / dl);
+        sv4[2] -= mu * dxi / sl;
+        sv4[3] -= mu * log(sl);
+      }
+      if (u < 1e300) {
+        const double su = u - W.x[i], z = W.zU[i];
+        du = mu / su - z + z / su * dxi;
+        if (dxi > 0) sv4[0] = fmin(sv4[0], tau * su / dxi);
+        if (du < 0) sv4[1] = fmin(sv4[1], -tau * z / du);
+        sv4[2] += mu * dxi / su;
+        sv4[3] -= mu * log(su);
+      }
+      W.dzL[i] = dl; W.dzU[i] = du;
+    }
+    {
+      const int ops[4] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM};
+      block_reduce<4>(cx, sv4, ops);
+    }
+    const double apr = sv4[0], adu = sv4[1], dphi = sv4[2], phi_cur = fval + sv4[3];
+    // ---- filter line search (Waechter & Biegler 2006, Alg. A, without restoration phase / SOC)
+    double alpha = apr;
+    bool accepted = false, ftype = false;
+    const int nfilt = S.flag[1];
+    for (int ls = 0; ls < 40; ls++, alpha *= 0.5) {
+      PAR_FOR(i, n) W.xt[i] = W.x[i] + alpha * W.dx[i];
+      PAR_FOR(i, nd) W.st[i] = W.s[i] + alpha * W.ds[i];
+      BMPC_SYNC();
+      eval_values(cx, C, W, p, W.xt, W.ct, W.dtr);
+      double tv2[2] = {0.0, 0.0};   // theta_trial, phi_trial
+      PAR_FOR(i, ne) tv2[0] += fabs(W.ct[i]);
+      PAR_FOR(i, nd) { tv2[0] += fabs(W.dtr[i] + W.st[i]); tv2[1] -= mu * log(W.st[i]); }
+      PAR_FOR(i, n) {
+        const int a = i % NX;
+        const double l = C.lb[a], u = C.ub[a];
+        if (l > -1e300) tv2[1] -= mu * log(W.xt[i] - l);
+        if (u < 1e300) tv2[1] -= mu * log(u - W.xt[i]);
+      }
+      PAR_FOR(k, N) tv2[1] += W.cost[k];
+      {
+        const int ops[2] = {RED_SUM, RED_SUM};
+        block_reduce<2>(cx, tv2, ops);
+      }
+      const double th_t = tv2[0], ph_t = tv2[1];
+      if (!(th_t == th_t) || !(ph_t == ph_t) || !(th_t < 1e300) || !(fabs(ph_t) < 1e300) || th_t > theta_max) continue;
+      bool filt_ok = true;
+      for (int q = 0; q < nfilt; q++)
+        if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }
+      if (!filt_ok) continue;
+      const bool sw = dphi < 0 && alpha * pow(-dphi, C.s_phi) > pow(th_cur, C.s_theta);
+      if (th_cur <= theta_min && sw) {
+        if (ph_t <= phi_cur + C.eta_phi * alpha * dphi) { accepted = true; ftype = true; break; }
+      } else {
+        if (th_t <= (1 - C.gamma_theta) * th_cur || ph_t <= phi_cur - C.gamma_phi * th_cur) { accepted = true; ftype = false; break; }
+      }
+    }
+    if (!accepted) {
+      // no restoration phase: clear the filter and take a strongly damped interior step
+      alpha = apr * 0.015625;
+      if (++ls_fail > 8) { status = ST_LINESEARCH; break; }
+      BMPC_SYNC();
+      if (cx.tid == 0) S.flag[1] = 0;
+    } else if (!ftype) {
+      BMPC_SYNC();
+      if (cx.tid == 0) {
+        int q = S.flag[1];
+        if (q >= 64) { for (int e = 0; e < 126; e++) S.filt[e] = S.filt[e + 2]; q = 63; }
+        S.filt[2 * q] = (1 - C.gamma_theta) * th_cur;
+        S.filt[2 * q + 1] = phi_cur - C.gamma_phi * th_cur;
+        S.flag[1] = q + 1;
+      }
+    }
+    // ---- accept the step; keep the multipliers within Ipopt's kappa_Sigma band
+    const double ks = 1e10;
+    PAR_FOR(i, n) {
+      const int a = i % NX;
+      const double l = C.lb[a], u = C.ub[a];
+      const double xn = W.x[i] + alpha * W.dx[i];
+      W.x[i] = xn;
+      if (l > -1e300) { const double sl = xn - l; double z = W.zL[i] + adu * W.dzL[i]; W.zL[i] = fmax(fmin(z, ks * mu / sl), mu / (ks * sl)); }
+      if (u < 1e300) { const double su = u - xn; double z = W.zU[i] + adu * W.dzU[i]; W.zU[i] = fmax(fmin(z, ks * mu / su), mu / (ks * su)); }
+    }
+    PAR_FOR(i, nd) {
+      const double sn = W.s[i] + alpha * W.ds[i];
+      W.s[i] = sn;
+      const double z = W.zs[i] + adu * W.dzs[i];
+      W.zs[i] = fmax(fmin(z, ks * mu / sn), mu / (ks * sn));
+    }
+    PAR_FOR(i, ne) W.y[i] += alpha * (W.ynew[i] - W.y[i]);
+    BMPC_SYNC();
+  }
+
+  // ---- report in the reference's conventions: x, g, lam_g, lam_x (CasADi: L = f + lam_g.g + lam_x.x)
+  BMPC_SYNC();
+  phase_path<2>(cx, C, W, p, W.x, W.dtr, W.st);   // W.st[0..7N) <- reference-form rows 36..42
+  BMPC_SYNC();
+  PAR_FOR(i, n) {
+    io.x[i] = W.x[i];
+    io.lam_x[i] = W.zU[i] - W.zL[i];
+  }
+  PAR_FOR(i, NG * N) {
+    const int k = i / NG, r = i - NG * k;
+    if (r < NE) { io.g[i] = W.c[NE * k + r]; io.lam_g[i] = W.y[NE * k + r]; }
+    else {
+      const int q = r - NE;
+      io.g[i] = W.st[NQ * k + q];
+      const double* z = W.zs + ND * k;
+      const double* dd = W.dtr + ND * k;
+      if (q < 2) io.lam_g[i] = z[q];
+      else {
+        const int j = 2 * (q - 1);
+        const double h = -0.5 * (dd[j] + dd[j + 1]);
+        io.lam_g[i] = (z[j] + z[j + 1]) / (2.0 * h);
+      }
+    }
+  }
+  if (cx.tid == 0) { *io.f = fval; *io.kkt = kkt_final; *io.iters = it; *io.status = status; }
+  BMPC_SYNC();
+}
+
+}  // namespace bmpc

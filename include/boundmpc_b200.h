@@ -1,0 +1,110 @@
+/* boundmpc_b200 — C ABI of the B200-native batched solver for BoundMPC's per-step OCP.
+ *
+ * This is the drop-in boundary for the hot path of Thieso/BoundMPC: the handle replaces the
+ * object returned by `casadi.nlpsol('solver', 'ipopt', prob, opts)`
+ * (bound_mpc/bound_mpc/BoundMPC/casadi_ocp_formulation.py:389, obtained in BoundMPC.py:150-161)
+ * and `bmpc_solve_batch*` replaces the call
+ *     sol = self.solver(x0=w0, lbx=self.lbu, ubx=self.ubu, lbg=self.lbg, ubg=self.ubg, p=params)
+ *     stats = self.solver.stats()
+ * (BoundMPC.py:446-457) for a batch of independent instances.  Plain C types only; the
+ * caller owns every buffer; nothing is allocated per call by the device-pointer entry.
+ * All functions return 0 on success and a negative code otherwise (never throw);
+ * `bmpc_last_error()` describes the last failure of the calling thread.
+ *
+ * Layouts (row-major, fp64): x0, x, lam_x: [batch, n], n = 44 N   (casadi_ocp_formulation.py:90-153)
+ *                            p: [batch, np], np = 141 + 91 nr_segs (casadi_ocp_formulation.py:361-376)
+ *                            g, lam_g: [batch, m], m = 43 N        (casadi_ocp_formulation.py:271-349)
+ * Sign conventions follow CasADi: L = f + lam_g . g + lam_x . x.
+ */
+#ifndef BOUNDMPC_B200_H
+#define BOUNDMPC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bmpc_handle bmpc_handle;
+
+/* Arguments of `setup_optimization_problem(N, nr_joints, nr_segs, dt, u_min, u_max, ut_min, ut_max,
+ * q_lim_lower, q_lim_upper, dq_lim_lower, dq_lim_upper, solver_opts)` (casadi_ocp_formulation.py:9-11)
+ * plus the Ipopt options the reference sets (BoundMPC.py:120-141).  nr_joints is fixed to 7. */
+typedef struct bmpc_config {
+  int32_t N;            /* horizon length (params.n) */
+  int32_t nr_segs;      /* path segments in the window */
+  double dt;            /* sample time */
+  double u_min, u_max;  /* joint jerk bounds */
+  double ut_min, ut_max;/* path-parameter jerk bounds */
+  double q_lim_lower[7], q_lim_upper[7];
+  double dq_lim_lower[7], dq_lim_upper[7];
+  double tol;           /* termination tolerance on Ipopt's scaled error (<= 0: 1e-8) */
+  int32_t max_iter;     /* <= 0: 500 (BoundMPC.py:122) */
+  double mu_init;       /* <= 0: 0.1 */
+  double bound_push;    /* <= 0: 1e-3 (Ipopt warm_start_bound_push) */
+  int32_t device;       /* CUDA device ordinal, -1: current device */
+  int32_t threads;      /* threads per CTA, <= 0: default */
+} bmpc_config;
+
+/* status codes written to `status[]` (stats()['success'] == (status == 0), BoundMPC.py:456-465) */
+#define BMPC_STATUS_SUCCESS 0
+#define BMPC_STATUS_MAXITER 1
+#define BMPC_STATUS_LINESEARCH 2
+#define BMPC_STATUS_REGULARIZATION 3
+#define BMPC_STATUS_NUMERIC 4
+
+/* error codes */
+#define BMPC_OK 0
+#define BMPC_E_INVALID (-1)
+#define BMPC_E_CUDA (-2)
+#define BMPC_E_NOMEM (-3)
+
+/* replaces: ca.nlpsol(...) at casadi_ocp_formulation.py:389 */
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
+void bmpc_destroy(bmpc_handle* h);
+
+/* n, m, np of the NLP (len(lbu), len(lbg), params.shape) */
+int bmpc_dims(const bmpc_handle* h, int32_t* n, int32_t* m, int32_t* np);
+
+/* replaces: the lbu, ubu, lbg, ubg lists returned by setup_optimization_problem
+ * (casadi_ocp_formulation.py:384-391).  Host arrays of length n, n, m, m. */
+int bmpc_bounds(const bmpc_handle* h, double* lbx, double* ubx, double* lbg, double* ubg);
+
+/* bytes of device scratch `bmpc_solve_batch` needs for `batch` instances */
+int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes);
+
+/* replaces: self.solver(x0=..., p=...) + self.solver.stats() (BoundMPC.py:446-457), batched.
+ * All data pointers are DEVICE pointers; `workspace` is device memory of at least
+ * bmpc_workspace_bytes(); `cuda_stream` is a cudaStream_t (NULL: default stream).
+ * Asynchronous with respect to the host.  f, iters, status, kkt_err may not be NULL. */
+int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g,
+                     double* lam_g, double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err,
+                     void* workspace, void* cuda_stream);
+
+/* Same call with HOST pointers (what a Python / ROS caller holds): copies x0 and p to the
+ * device, solves, copies the results back and synchronises.  Device buffers are owned and
+ * cached by the handle.  Any output pointer except x, iters, status may be NULL. */
+int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g,
+                          double* lam_g, double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err);
+
+/* Evaluation of the NLP functions for parity tests (what CasADi's nlp_f, nlp_g, nlp_grad_f,
+ * nlp_jac_g, nlp_hess_l provide, casadi_ocp_formulation.py:389), HOST pointers, small batches.
+ *   lam   [batch, 48 N]: per stage 36 equality multipliers then 12 interval-row multipliers
+ *   f     [batch]         g      [batch, m]   (reference form)
+ *   d     [batch, 12 N]   interval-form inequality rows
+ *   grad  [batch, n]      jac    [batch, 48 N, n]  rows per stage: 36 equality rows, 12 interval rows
+ *   hess  [batch, n, n]   Hessian of f + lam . (c, d)
+ * Output pointers may be NULL. */
+int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const double* p, const double* lam,
+                         double* f, double* g, double* d, double* grad, double* jac, double* hess);
+
+/* name and duration of the kernels launched by the last solve on this handle (diagnostics):
+ * number of kernel launches issued by this library since the handle was created */
+int64_t bmpc_launch_count(const bmpc_handle* h);
+
+const char* bmpc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

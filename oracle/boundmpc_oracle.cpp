@@ -787,6 +787,44 @@ int orc_derivs(int N, int S, double dt, const double* x, const double* p, const 
   return 0;
 }
 
+// interval-form derivatives (the form the interior-point iteration works on):
+// lam [48 N] per stage 36 equality + 12 interval multipliers; jac [48 N x n]; hess of f + lam.(c,d)
+int orc_derivs_interval(int N, int S, double dt, const double* x, const double* p, const double* lam,
+                        double* d, double* gradf, double* jac, double* hess) {
+  Prob P(N, S, dt);
+  Eval E(N);
+  eval_full(P, x, p, lam, E, true);
+  int n = P.n;
+  const int NL = NE + ND;
+  for (int i = 0; i < ND * N; i++) d[i] = E.d[i];
+  for (int i = 0; i < n; i++) gradf[i] = E.gradf[i];
+  memset(jac, 0, sizeof(double) * NL * N * n);
+  for (int k = 0; k < N; k++) {
+    for (int i = 0; i < NE; i++) {
+      double* row = jac + (size_t)(NL * k + i) * n;
+      if (k > 0) for (int j = 0; j < NX; j++) row[NX * (k - 1) + j] = E.A[(k * NE + i) * NX + j];
+      for (int j = 0; j < 8; j++) row[NX * k + j] = E.B[(k * NE + i) * 8 + j];
+      row[NX * k + 8 + i] = -1.0;
+    }
+    for (int i = 0; i < ND; i++) {
+      double* row = jac + (size_t)(NL * k + NE + i) * n;
+      for (int j = 0; j < NX; j++) row[NX * k + j] = E.Jd[(k * ND + i) * NX + j];
+    }
+  }
+  memset(hess, 0, sizeof(double) * n * n);
+  for (int k = 0; k < N; k++)
+    for (int i = 0; i < NX; i++)
+      for (int j = 0; j < NX; j++) {
+        hess[(size_t)(NX * k + i) * n + NX * k + j] = E.Wd[k * NX * NX + i * NX + j];
+        if (k > 0) {
+          double v = E.Wo[k * NX * NX + i * NX + j];
+          hess[(size_t)(NX * k + i) * n + NX * (k - 1) + j] = v;
+          hess[(size_t)(NX * (k - 1) + j) * n + NX * k + i] = v;
+        }
+      }
+  return 0;
+}
+
 // opts: [tol, max_iter, mu_init, bound_push, verbose]
 int orc_solve(int N, int S, double dt, const double* x0, const double* p, const double* opts,
               double* x, double* g, double* lam_g, double* lam_x, double* f, int* iters, double* kkt) {

@@ -73,3 +73,14 @@ def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=0.1, bound_p
     st = lib().orc_solve(N, S, ctypes.c_double(dt), _p(x0), _p(p), _p(opts), _p(x), _p(g), _p(lam_g), _p(lam_x),
                          ctypes.byref(f), ctypes.byref(it), ctypes.byref(kkt))
     return dict(x=x, g=g, lam_g=lam_g, lam_x=lam_x, f=f.value, iters=it.value, kkt=kkt.value, status=st)
+
+
+def derivs_interval(x, p, lam, N=10, S=4, dt=0.1):
+    """Interval-form rows: d [12N], grad f [n], jac [48N, n], hess of f + lam.(c, d) [n, n]."""
+    n, m, _ = dims(N, S)
+    x = np.ascontiguousarray(x, float)
+    p = np.ascontiguousarray(p, float)
+    lam = np.ascontiguousarray(lam, float)
+    d, grad, jac, hess = np.empty(12 * N), np.empty(n), np.empty((48 * N, n)), np.empty((n, n))
+    lib().orc_derivs_interval(N, S, ctypes.c_double(dt), _p(x), _p(p), _p(lam), _p(d), _p(grad), _p(jac), _p(hess))
+    return d, grad, jac, hess

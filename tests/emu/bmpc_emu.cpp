@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE — host emulation build of the CUDA solver source.
+// Compiles boundmpc_b200/csrc/*.cuh with BMPC_HOST_EMU (one "thread" per CTA, phases run
+// sequentially) so that the kernel source can be checked against the oracle on machines
+// without a GPU.  Never part of the product library and never loaded by boundmpc_b200.
+#define BMPC_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../boundmpc_b200/csrc/bmpc_host.h"
+#include "../../boundmpc_b200/csrc/bmpc_eval.cuh"
+
+using namespace bmpc;
+
+extern "C" {
+
+int emu_solve(const bmpc_config* cfg, int batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+              double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  std::vector<double> ws(work_doubles(C.N));
+  Smem* S = new Smem;
+  Work W;
+  work_carve(W, ws.data(), C.N);
+  Ctx cx{0, 1, S->red};
+  for (int b = 0; b < batch; b++) {
+    InstanceIO io{x0 + (size_t)b * C.n, p + (size_t)b * C.np, x + (size_t)b * C.n, g + (size_t)b * C.m,
+                  lam_g + (size_t)b * C.m, lam_x + (size_t)b * C.n, f + b, kkt + b, iters + b, status + b};
+    solve_instance(cx, C, W, *S, io);
+  }
+  delete S;
+  return 0;
+}
+
+int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p, const double* lam, double* f, double* g,
+             double* d, double* grad, double* jac, double* hess) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  std::vector<double> ws(work_doubles(C.N));
+  Smem* S = new Smem;
+  Work W;
+  work_carve(W, ws.data(), C.N);
+  Ctx cx{0, 1, S->red};
+  const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
+  for (int b = 0; b < batch; b++) {
+    EvalIO io{x + b * n, p + (size_t)b * C.np, lam ? lam + b * nl : nullptr, f ? f + b : nullptr, g ? g + (size_t)b * C.m : nullptr,
+              d ? d + (size_t)b * ND * C.N : nullptr, grad ? grad + b * n : nullptr, jac ? jac + b * nl * n : nullptr,
+              hess ? hess + b * n * n : nullptr};
+    eval_instance(cx, C, W, *S, io);
+  }
+  delete S;
+  return 0;
+}
+}

@@ -1,0 +1,81 @@
+"""ctypes wrapper of the host-emulation build of the kernel source.  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libbmpc_emu.so")
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int32), ("nr_segs", ctypes.c_int32), ("dt", ctypes.c_double),
+                ("u_min", ctypes.c_double), ("u_max", ctypes.c_double), ("ut_min", ctypes.c_double), ("ut_max", ctypes.c_double),
+                ("q_lim_lower", ctypes.c_double * 7), ("q_lim_upper", ctypes.c_double * 7),
+                ("dq_lim_lower", ctypes.c_double * 7), ("dq_lim_upper", ctypes.c_double * 7),
+                ("tol", ctypes.c_double), ("max_iter", ctypes.c_int32), ("mu_init", ctypes.c_double),
+                ("bound_push", ctypes.c_double), ("device", ctypes.c_int32), ("threads", ctypes.c_int32)]
+
+
+def make_cfg(N=10, S=4, dt=0.1, tol=1e-8, max_iter=500):
+    from boundmpc_b200 import robot_model as rm
+    c = Cfg()
+    c.N, c.nr_segs, c.dt = N, S, dt
+    c.u_min, c.u_max, c.ut_min, c.ut_max = rm.U_MIN, rm.U_MAX, rm.U_MIN, rm.U_MAX
+    for i in range(7):
+        c.q_lim_lower[i], c.q_lim_upper[i] = rm.Q_LIM_LOWER[i], rm.Q_LIM_UPPER[i]
+        c.dq_lim_lower[i], c.dq_lim_upper[i] = rm.DQ_LIM_LOWER[i], rm.DQ_LIM_UPPER[i]
+    c.tol, c.max_iter, c.mu_init, c.bound_push, c.device, c.threads = tol, max_iter, 0.0, 0.0, -1, 0
+    return c
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, "bmpc_emu.cpp")] + [os.path.join(_ROOT, "boundmpc_b200", "csrc", f) for f in
+           ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, src[0]])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500):
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), float)
+    p = np.ascontiguousarray(np.atleast_2d(p), float)
+    B, n = x0.shape
+    m = 43 * N
+    cfg = make_cfg(N, S, dt, tol, max_iter)
+    x, g, lg, lx = np.empty((B, n)), np.empty((B, m)), np.empty((B, m)), np.empty((B, n))
+    f, kkt = np.empty(B), np.empty(B)
+    it, st = np.empty(B, np.int32), np.empty(B, np.int32)
+    rc = lib().emu_solve(ctypes.byref(cfg), B, _p(x0), _p(p), _p(x), _p(g), _p(lg), _p(lx), _p(f),
+                         it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _p(kkt))
+    assert rc == 0
+    return dict(x=x, g=g, lam_g=lg, lam_x=lx, f=f, iters=it, status=st, kkt=kkt)
+
+
+def evaluate(x, p, lam=None, N=10, S=4, dt=0.1):
+    x = np.ascontiguousarray(np.atleast_2d(x), float)
+    p = np.ascontiguousarray(np.atleast_2d(p), float)
+    B, n = x.shape
+    m = 43 * N
+    cfg = make_cfg(N, S, dt)
+    lam = None if lam is None else np.ascontiguousarray(np.atleast_2d(lam), float)
+    f, g, d, grad = np.empty(B), np.empty((B, m)), np.empty((B, 12 * N)), np.empty((B, n))
+    jac, hess = np.empty((B, 48 * N, n)), np.empty((B, n, n))
+    rc = lib().emu_eval(ctypes.byref(cfg), B, _p(x), _p(p), _p(lam), _p(f), _p(g), _p(d), _p(grad), _p(jac), _p(hess))
+    assert rc == 0
+    return dict(f=f, g=g, d=d, grad=grad, jac=jac, hess=hess)
