@@ -14,10 +14,12 @@
 
 #ifdef BMPC_HOST_EMU
 #define BMPC_DEV inline
+#define BMPC_HD inline
 #define BMPC_SYNC() ((void)0)
 #define BMPC_LDG(ptr) (*(ptr))
 #else
 #define BMPC_DEV __device__ __forceinline__
+#define BMPC_HD __host__ __device__ inline
 #define BMPC_SYNC() __syncthreads()
 #define BMPC_LDG(ptr) __ldg(ptr)
 #endif
@@ -51,7 +53,7 @@ struct PLayout {
   int q0, dq0, ddq0, phi0, p0, v0, iwref, dtau, par, orth1, orth2, xphid, jerk, phisw, jacr, jacl;
   int pref, dpref, dpn, bp1, bp2, br1, br2, a4, a3, a2, a1, a0, w, phimax, dphimax, v1, v2, v3, qd;
 };
-BMPC_DEV PLayout make_layout(int S) {
+BMPC_HD PLayout make_layout(int S) {
   PLayout L;
   L.S = S;
   L.q0 = 0; L.dq0 = 7; L.ddq0 = 14; L.phi0 = 21; L.p0 = 24; L.v0 = 30; L.iwref = 36; L.dtau = 39; L.par = 42;

@@ -21,7 +21,7 @@ inline int make_config(const bmpc_config& in, Config& C) {
   }
   C.lb[oUPHI] = in.ut_min; C.ub[oUPHI] = in.ut_max;
   C.lb[oPHI] = 0.0;
-  C.tol = in.tol > 0 ? in.tol : 1e-8;
+  C.tol = in.tol > 0 ? in.tol : 1e-9;
   C.max_iter = in.max_iter > 0 ? in.max_iter : 500;
   C.mu_init = in.mu_init > 0 ? in.mu_init : 0.1;
   C.bound_push = in.bound_push > 0 ? in.bound_push : 1e-3;

@@ -1,0 +1,262 @@
+// boundmpc_b200 — CUDA kernels (sm_100a) and the C ABI declared in include/boundmpc_b200.h.
+//
+// k_solve: persistent CTAs, one OCP instance per CTA at a time, instances pulled from an
+// atomic work queue so that instances with few interior-point iterations free their SM early
+// (SURVEY 7.1 K0-K5).  Per-CTA state lives in a global workspace slice that stays L2-resident;
+// the Riccati blocks are staged in shared memory (struct Smem).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "bmpc_host.h"
+#include "bmpc_eval.cuh"
+
+using namespace bmpc;
+
+#ifndef BMPC_MAX_THREADS
+#define BMPC_MAX_THREADS 256
+#endif
+
+struct BatchIO {
+  const double* x0; const double* p;
+  double *x, *g, *lam_g, *lam_x, *f, *kkt;
+  int32_t *iters, *status;
+};
+
+__global__ void __launch_bounds__(BMPC_MAX_THREADS) k_solve(const __grid_constant__ Config C, int batch, BatchIO io, double* ws,
+                                                            size_t ws_stride, unsigned int* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
+  Work W;
+  work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  for (;;) {
+    if (threadIdx.x == 0) S.flag[2] = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int b = S.flag[2];
+    __syncthreads();
+    if (b >= batch) break;
+    InstanceIO ii{io.x0 + (size_t)b * C.n, io.p + (size_t)b * C.np, io.x + (size_t)b * C.n, io.g + (size_t)b * C.m,
+                  io.lam_g + (size_t)b * C.m, io.lam_x + (size_t)b * C.n, io.f + b, io.kkt + b, io.iters + b, io.status + b};
+    solve_instance(cx, C, W, S, ii);
+  }
+}
+
+struct EvalBatchIO {
+  const double *x, *p, *lam;
+  double *f, *g, *d, *grad, *jac, *hess;
+};
+
+__global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant__ Config C, int batch, EvalBatchIO io, double* ws,
+                                                           size_t ws_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
+  Work W;
+  work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    EvalIO e{io.x + b * n, io.p + (size_t)b * C.np, io.lam ? io.lam + b * nl : nullptr, io.f ? io.f + b : nullptr,
+             io.g ? io.g + (size_t)b * C.m : nullptr, io.d ? io.d + (size_t)b * ND * C.N : nullptr, io.grad ? io.grad + b * n : nullptr,
+             io.jac ? io.jac + b * nl * n : nullptr, io.hess ? io.hess + b * n * n : nullptr};
+    eval_instance(cx, C, W, S, e);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+#define CU(call)                                                                  \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return fail(BMPC_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+struct bmpc_handle {
+  Config C;
+  int device, threads, sms, ctas_per_sm;
+  size_t ws_stride;    // doubles per CTA slot
+  int64_t launches;
+  // cached device buffers of the host-pointer entry points
+  void* dbuf; size_t dbuf_bytes;
+  cudaStream_t stream;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int grid_for(const bmpc_handle* h, int batch) {
+  int g = h->sms * h->ctas_per_sm;
+  return batch < g ? batch : g;
+}
+
+extern "C" {
+
+const char* bmpc_last_error(void) { return g_err; }
+
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
+  if (!cfg || !out) return fail(BMPC_E_INVALID, "bmpc_create: null argument");
+  bmpc_handle* h = new (std::nothrow) bmpc_handle();
+  if (!h) return fail(BMPC_E_NOMEM, "bmpc_create: out of memory");
+  if (make_config(*cfg, h->C)) { delete h; return fail(BMPC_E_INVALID, "bmpc_create: invalid N / nr_segs / dt"); }
+  int dev = cfg->device;
+  if (dev < 0) { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); } }
+  h->device = dev;
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  h->sms = prop.multiProcessorCount;
+  h->threads = cfg->threads > 0 ? cfg->threads : BMPC_MAX_THREADS;
+  if (h->threads > BMPC_MAX_THREADS || h->threads % 32) { delete h; return fail(BMPC_E_INVALID, "bmpc_create: threads must be a multiple of 32 and <= 256"); }
+  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, h->threads, sizeof(Smem));
+  if (e != cudaSuccess || occ < 1) { delete h; return fail(BMPC_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
+  const char* env = getenv("BMPC_CTAS_PER_SM");
+  h->ctas_per_sm = env ? atoi(env) : occ;
+  if (h->ctas_per_sm < 1) h->ctas_per_sm = 1;
+  if (h->ctas_per_sm > occ) h->ctas_per_sm = occ;
+  h->ws_stride = align_up(work_doubles(h->C.N), 32);
+  h->launches = 0;
+  h->dbuf = nullptr; h->dbuf_bytes = 0;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return BMPC_OK;
+}
+
+void bmpc_destroy(bmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->dbuf) cudaFree(h->dbuf);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int bmpc_dims(const bmpc_handle* h, int32_t* n, int32_t* m, int32_t* np) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_dims: null handle");
+  if (n) *n = h->C.n;
+  if (m) *m = h->C.m;
+  if (np) *np = h->C.np;
+  return BMPC_OK;
+}
+
+int bmpc_bounds(const bmpc_handle* h, double* lbx, double* ubx, double* lbg, double* ubg) {
+  if (!h || !lbx || !ubx || !lbg || !ubg) return fail(BMPC_E_INVALID, "bmpc_bounds: null argument");
+  fill_bounds(h->C, lbx, ubx, lbg, ubg);
+  return BMPC_OK;
+}
+
+int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes) {
+  if (!h || !bytes || batch < 0) return fail(BMPC_E_INVALID, "bmpc_workspace_bytes: invalid argument");
+  *bytes = 256 + (size_t)grid_for(h, batch > 0 ? batch : 1) * h->ws_stride * sizeof(double);
+  return BMPC_OK;
+}
+
+int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+
+int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+                     double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err, void* workspace, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch: null handle");
+  if (batch < 0 || !x0 || !p || !x || !g || !lam_g || !lam_x || !f || !iters || !status || !kkt_err || !workspace)
+    return fail(BMPC_E_INVALID, "bmpc_solve_batch: null buffer");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  unsigned int* counter = (unsigned int*)workspace;
+  double* ws = (double*)((char*)workspace + 256);
+  CU(cudaMemsetAsync(counter, 0, 256, st));
+  BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status};
+  const int grid = grid_for(h, batch);
+  k_solve<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, counter);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+static int ensure_dbuf(bmpc_handle* h, size_t bytes) {
+  if (h->dbuf_bytes >= bytes) return BMPC_OK;
+  if (h->dbuf) { cudaFree(h->dbuf); h->dbuf = nullptr; h->dbuf_bytes = 0; }
+  CU(cudaMalloc(&h->dbuf, bytes));
+  h->dbuf_bytes = bytes;
+  return BMPC_OK;
+}
+
+int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+                          double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null handle");
+  if (batch < 0 || !x0 || !p || !x || !iters || !status) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null buffer");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np;
+  size_t wsb = 0;
+  bmpc_workspace_bytes(h, batch, &wsb);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_x0 = take(B * n * 8), o_p = take(B * np * 8), o_x = take(B * n * 8), o_g = take(B * m * 8), o_lg = take(B * m * 8),
+               o_lx = take(B * n * 8), o_f = take(B * 8), o_k = take(B * 8), o_it = take(B * 4), o_st = take(B * 4), o_ws = take(wsb);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(d + o_x0, x0, B * n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
+  rc = bmpc_solve_batch(h, batch, (double*)(d + o_x0), (double*)(d + o_p), (double*)(d + o_x), (double*)(d + o_g), (double*)(d + o_lg),
+                        (double*)(d + o_lx), (double*)(d + o_f), (int32_t*)(d + o_it), (int32_t*)(d + o_st), (double*)(d + o_k), d + o_ws, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(x, d + o_x, B * n * 8, cudaMemcpyDeviceToHost, st));
+  if (g) CU(cudaMemcpyAsync(g, d + o_g, B * m * 8, cudaMemcpyDeviceToHost, st));
+  if (lam_g) CU(cudaMemcpyAsync(lam_g, d + o_lg, B * m * 8, cudaMemcpyDeviceToHost, st));
+  if (lam_x) CU(cudaMemcpyAsync(lam_x, d + o_lx, B * n * 8, cudaMemcpyDeviceToHost, st));
+  if (f) CU(cudaMemcpyAsync(f, d + o_f, B * 8, cudaMemcpyDeviceToHost, st));
+  if (kkt_err) CU(cudaMemcpyAsync(kkt_err, d + o_k, B * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(iters, d + o_it, B * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return BMPC_OK;
+}
+
+int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const double* p, const double* lam, double* f, double* g,
+                         double* d_out, double* grad, double* jac, double* hess) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_eval_batch_host: null handle");
+  if (batch < 0 || !x || !p) return fail(BMPC_E_INVALID, "bmpc_eval_batch_host: null buffer");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np, nl = (size_t)(NE + ND) * h->C.N, ndd = (size_t)ND * h->C.N;
+  const int grid = grid_for(h, batch);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_x = take(B * n * 8), o_p = take(B * np * 8), o_l = take(B * nl * 8), o_f = take(B * 8), o_g = take(B * m * 8),
+               o_d = take(B * ndd * 8), o_gr = take(B * n * 8), o_j = take(jac ? B * nl * n * 8 : 8), o_h = take(hess ? B * n * n * 8 : 8),
+               o_ws = take((size_t)grid * h->ws_stride * 8);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(d + o_x, x, B * n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
+  if (lam) CU(cudaMemcpyAsync(d + o_l, lam, B * nl * 8, cudaMemcpyHostToDevice, st));
+  EvalBatchIO io{(double*)(d + o_x), (double*)(d + o_p), lam ? (double*)(d + o_l) : nullptr, (double*)(d + o_f), (double*)(d + o_g),
+                 (double*)(d + o_d), (double*)(d + o_gr), jac ? (double*)(d + o_j) : nullptr, hess ? (double*)(d + o_h) : nullptr};
+  k_eval<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, (double*)(d + o_ws), h->ws_stride);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  if (f) CU(cudaMemcpyAsync(f, d + o_f, B * 8, cudaMemcpyDeviceToHost, st));
+  if (g) CU(cudaMemcpyAsync(g, d + o_g, B * m * 8, cudaMemcpyDeviceToHost, st));
+  if (d_out) CU(cudaMemcpyAsync(d_out, d + o_d, B * ndd * 8, cudaMemcpyDeviceToHost, st));
+  if (grad) CU(cudaMemcpyAsync(grad, d + o_gr, B * n * 8, cudaMemcpyDeviceToHost, st));
+  if (jac) CU(cudaMemcpyAsync(jac, d + o_j, B * nl * n * 8, cudaMemcpyDeviceToHost, st));
+  if (hess) CU(cudaMemcpyAsync(hess, d + o_h, B * n * n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return BMPC_OK;
+}
+
+}  // extern "C"

@@ -45,7 +45,7 @@ struct Work {
   double *wp0;                                              // [44] stage-0 "previous block" built from p
 };
 
-BMPC_DEV size_t work_doubles(int N) {
+BMPC_HD size_t work_doubles(int N) {
   size_t n = (size_t)NX * N, ne = (size_t)NE * N, nd = (size_t)ND * N;
   return 9 * n + 4 * ne + 7 * nd + (size_t)N * R_SIZE + (size_t)2 * N * F_SIZE + (size_t)N * 8 * NX + (size_t)N * 8 + N + NX;
 }

@@ -38,7 +38,7 @@ typedef struct bmpc_config {
   double ut_min, ut_max;/* path-parameter jerk bounds */
   double q_lim_lower[7], q_lim_upper[7];
   double dq_lim_lower[7], dq_lim_upper[7];
-  double tol;           /* termination tolerance on Ipopt's scaled error (<= 0: 1e-8) */
+  double tol;           /* termination tolerance on Ipopt's scaled error (<= 0: 1e-9) */
   int32_t max_iter;     /* <= 0: 500 (BoundMPC.py:122) */
   double mu_init;       /* <= 0: 0.1 */
   double bound_push;    /* <= 0: 1e-3 (Ipopt warm_start_bound_push) */

@@ -20,7 +20,7 @@ class Cfg(ctypes.Structure):
                 ("bound_push", ctypes.c_double), ("device", ctypes.c_int32), ("threads", ctypes.c_int32)]
 
 
-def make_cfg(N=10, S=4, dt=0.1, tol=1e-8, max_iter=500):
+def make_cfg(N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
     from boundmpc_b200 import robot_model as rm
     c = Cfg()
     c.N, c.nr_segs, c.dt = N, S, dt
@@ -52,7 +52,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
-def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500):
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
     x0 = np.ascontiguousarray(np.atleast_2d(x0), float)
     p = np.ascontiguousarray(np.atleast_2d(p), float)
     B, n = x0.shape

@@ -1,0 +1,39 @@
+"""The C-ABI library: builds, loads, exports every symbol include/boundmpc_b200.h declares, and
+fails loudly (no fallback) where no CUDA device exists."""
+import os
+import re
+import ctypes
+import pytest
+import torch
+from boundmpc_b200 import _cabi, build as bld
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "boundmpc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bmpc_[a-z_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = bld.build()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    names = _declared_functions()
+    assert len(names) >= 9
+    for nm in names:
+        assert hasattr(L, nm), f"{nm} declared in include/boundmpc_b200.h but not exported"
+    assert sorted(_cabi.EXPORTS) == names
+
+
+def test_sm100a_code_is_in_the_library():
+    out = os.popen(f"cuobjdump -lelf {bld.build()} 2>/dev/null").read()
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_fails_loudly_without_gpu():
+    from boundmpc_b200.ocp import default_solver
+    with pytest.raises(_cabi.BmpcError):
+        default_solver()

@@ -1,0 +1,52 @@
+"""The CUDA solver *source* (boundmpc_b200/csrc/*.cuh) compiled for the host in emulation mode
+(tests/emu) against the oracle.  Runs without a GPU; the device build of the same source is
+checked by tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+from oracle import oracle as O
+from tests.emu import emu
+from tests.util import load, active_set, rel_q_error
+
+
+@pytest.mark.parametrize("scn", ["exp1", "exp2"])
+def test_eval_matches_oracle(scn):
+    G = load(f"nlp_{scn}.npz")
+    rng = np.random.default_rng(3)
+    for i in range(len(G["x"])):
+        x, p = G["x"][i], G["p"][i]
+        lam = rng.normal(size=480)
+        lam.reshape(10, 48)[:, 36:] = np.abs(lam.reshape(10, 48)[:, 36:])
+        e = emu.evaluate(x, p, lam)
+        assert abs(e["f"][0] - G["f"][i]) <= 1e-13 * abs(G["f"][i])
+        assert (np.abs(e["g"][0] - G["g"][i]) <= 1e-12 * np.maximum(1.0, np.abs(G["g"][i]))).all()
+        assert np.abs(e["grad"][0] - G["grad"][i]).max() <= 1e-11 * max(1.0, np.abs(G["grad"][i]).max())
+        d, grad, jac, hess = O.derivs_interval(x, p, lam)
+        assert (np.abs(e["d"][0] - d) <= 1e-12 * np.maximum(1.0, np.abs(d))).all()
+        assert np.abs(e["jac"][0] - jac).max() <= 1e-11 * max(1.0, np.abs(jac).max())
+        assert np.abs(e["hess"][0] - hess).max() <= 1e-11 * np.abs(hess).max()
+        # equality rows of the Jacobian against the reference-executed complex-step Jacobian
+        je = e["jac"][0].reshape(10, 48, 440)[:, :36].reshape(360, 440)
+        jr = G["jac"][i].reshape(10, 43, 440)[:, :36].reshape(360, 440)
+        assert np.abs(je - jr).max() <= 1e-9 * max(1.0, np.abs(jr).max())
+
+
+@pytest.mark.parametrize("scn", ["exp1", "exp2"])
+def test_solve_matches_golden(scn):
+    S = load(f"seq_{scn}.npz")
+    r = emu.solve(S["x0"], S["p"], tol=1e-9)
+    assert (r["status"] == 0).all()
+    assert (r["kkt"] <= 1e-9).all()
+    for i in range(len(S["step"])):
+        assert rel_q_error(r["x"][i], S["x"][i]) < 1e-6
+        assert np.abs(r["x"][i] - S["x"][i]).max() < 1e-5
+        assert abs(r["f"][i] - S["f"][i]) < 1e-7 * abs(S["f"][i])
+        assert active_set({"x": r["x"][i], "g": r["g"][i]}) == active_set({"x": S["x"][i], "g": S["g"][i]})
+
+
+def test_same_iterates_as_oracle():
+    S = load("seq_exp1.npz")
+    for i in (0, 4, 9):
+        ro = O.solve(S["x0"][i], S["p"][i], tol=1e-8)
+        re = emu.solve(S["x0"][i], S["p"][i], tol=1e-8)
+        assert ro["iters"] == re["iters"][0]
+        assert np.abs(ro["x"] - re["x"][0]).max() < 1e-8

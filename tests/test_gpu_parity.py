@@ -1,0 +1,105 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / golden fixtures.  GPU only."""
+import numpy as np
+import pytest
+import torch
+from tests.util import load, active_set, rel_q_error
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from boundmpc_b200.ocp import default_solver
+    return default_solver(N=10, nr_segs=4, dt=0.1)
+
+
+@pytest.mark.parametrize("scn", ["exp1", "exp2"])
+def test_eval_against_reference_executed_values(solver, scn):
+    from oracle import oracle as O
+    G = load(f"nlp_{scn}.npz")
+    rng = np.random.default_rng(5)
+    lam = rng.normal(size=(len(G["x"]), 480))
+    lam.reshape(-1, 10, 48)[:, :, 36:] = np.abs(lam.reshape(-1, 10, 48)[:, :, 36:])
+    e = solver.eval_batch(G["x"], G["p"], lam)
+    for i in range(len(G["x"])):
+        assert abs(e["f"][i] - G["f"][i]) <= 1e-12 * abs(G["f"][i])
+        assert (np.abs(e["g"][i] - G["g"][i]) <= 1e-11 * np.maximum(1.0, np.abs(G["g"][i]))).all()
+        assert np.abs(e["grad"][i] - G["grad"][i]).max() <= 1e-10 * max(1.0, np.abs(G["grad"][i]).max())
+        je = e["jac"][i].reshape(10, 48, 440)[:, :36].reshape(360, 440)
+        jr = G["jac"][i].reshape(10, 43, 440)[:, :36].reshape(360, 440)
+        assert np.abs(je - jr).max() <= 1e-9 * max(1.0, np.abs(jr).max())
+        d, grad, jac, hess = O.derivs_interval(G["x"][i], G["p"][i], lam[i])
+        assert (np.abs(e["d"][i] - d) <= 1e-11 * np.maximum(1.0, np.abs(d))).all()
+        assert np.abs(e["jac"][i] - jac).max() <= 1e-10 * max(1.0, np.abs(jac).max())
+        assert np.abs(e["hess"][i] - hess).max() <= 1e-10 * np.abs(hess).max()
+
+
+@pytest.mark.parametrize("scn", ["exp1", "exp2"])
+def test_solve_against_golden_kkt_points(solver, scn):
+    S = load(f"seq_{scn}.npz")
+    r = solver.solve_batch(S["x0"], S["p"])
+    assert (r["status"] == 0).all()
+    assert (r["kkt"] <= solver.tol).all()
+    for i in range(len(S["step"])):
+        assert rel_q_error(r["x"][i], S["x"][i]) < 1e-6           # north-star: primal joint trajectory <= 1e-6 relative
+        assert np.abs(r["x"][i] - S["x"][i]).max() < 1e-5
+        assert abs(r["f"][i] - S["f"][i]) < 1e-7 * abs(S["f"][i])
+        assert active_set({"x": r["x"][i], "g": r["g"][i]}) == active_set({"x": S["x"][i], "g": S["g"][i]})
+        g = r["g"][i].reshape(10, 43)
+        assert np.abs(g[:, :36]).max() < 1e-7 and g[:, 36:].max() < 1e-7
+
+
+def test_same_iterates_as_oracle(solver):
+    from oracle import oracle as O
+    S = load("seq_exp1.npz")
+    r = solver.solve_batch(S["x0"][:4], S["p"][:4])
+    for i in range(4):
+        ro = O.solve(S["x0"][i], S["p"][i], tol=solver.tol)
+        assert ro["iters"] == r["iters"][i]
+        assert np.abs(ro["x"] - r["x"][i]).max() < 1e-7
+
+
+def test_casadi_like_call_surface(solver):
+    S = load("seq_exp1.npz")
+    lbx, ubx, lbg, ubg = solver.bounds()
+    sol = solver(x0=S["x0"][0].tolist(), lbx=lbx.tolist(), ubx=ubx.tolist(), lbg=lbg.tolist(), ubg=ubg.tolist(), p=S["p"][0])
+    st = solver.stats()
+    assert st["success"] and st["return_status"] == "Solve_Succeeded" and st["iter_count"] > 5
+    assert sol["x"].shape == (440,) and sol["g"].shape == (430,) and sol["lam_g"].shape == (430,) and sol["lam_x"].shape == (440,)
+    # the reference's own feasibility check (BoundMPC.py:461-465)
+    g = sol["g"]
+    viol = -np.sum(g[np.where(g < lbg - 1e-6)[0]]) + np.sum(g[np.where(g > ubg + 1e-6)[0]])
+    assert viol < 1e-4
+    assert abs(sol["f"] - 1963.4557512307) < 1e-6
+
+
+def test_batch_determinism_and_device_entry(solver):
+    S = load("seq_exp2.npz")
+    reps = 40
+    x0 = np.tile(S["x0"], (reps, 1))
+    p = np.tile(S["p"], (reps, 1))
+    a = solver.solve_batch(x0, p)
+    nb = len(S["step"])
+    for k in ("x", "lam_g", "lam_x", "f"):
+        ref = a[k][:nb]
+        assert np.array_equal(a[k].reshape(reps, *ref.shape), np.broadcast_to(ref, (reps, *ref.shape)))   # bitwise
+    xd = torch.from_numpy(x0).cuda()
+    pd = torch.from_numpy(p).cuda()
+    b = solver.solve_batch(xd, pd)
+    torch.cuda.synchronize()
+    assert np.array_equal(b["x"].cpu().numpy(), a["x"])
+    assert np.array_equal(b["iters"].cpu().numpy(), a["iters"])
+
+
+def test_edge_cases(solver):
+    S = load("seq_exp1.npz")
+    r0 = solver.solve_batch(np.empty((0, 440)), np.empty((0, 505)))
+    assert r0["x"].shape == (0, 440)
+    with pytest.raises(ValueError):
+        solver.solve_batch(S["x0"][:2], S["p"][:3])
+    # a start far outside the bounds is pushed inside and still converges to the same point
+    x0 = S["x0"][0].copy()
+    x0[8:15] += 10.0
+    r = solver.solve_batch(x0[None], S["p"][:1])
+    assert r["status"][0] == 0
+    assert rel_q_error(r["x"][0], S["x"][0]) < 1e-6
