@@ -47,7 +47,7 @@ class BatchSolver:
         cfg.mu_init = float(opts.get("mu_init", 0.0))
         cfg.bound_push = float(opts.get("warm_start_bound_push", 0.0))
         cfg.device = int(device)
-        cfg.threads = int(opts.get("threads", 0))
+        cfg.threads = int((solver_opts or {}).get("b200", {}).get("threads", 0))
         self._lib = _cabi.lib()
         h = ctypes.c_void_p()
         _cabi.check(self._lib.bmpc_create(ctypes.byref(cfg), ctypes.byref(h)), "bmpc_create")

@@ -97,9 +97,10 @@ def test_edge_cases(solver):
     assert r0["x"].shape == (0, 440)
     with pytest.raises(ValueError):
         solver.solve_batch(S["x0"][:2], S["p"][:3])
-    # a start far outside the bounds is pushed inside and still converges to the same point
+    # a start outside the bounds is pushed inside and still converges to the same point
     x0 = S["x0"][0].copy()
-    x0[8:15] += 10.0
+    x0[15:22] = 3.0            # dq guess beyond every velocity limit at stage 0
+    x0[41::44] = -0.1          # negative path parameter
     r = solver.solve_batch(x0[None], S["p"][:1])
     assert r["status"][0] == 0
     assert rel_q_error(r["x"][0], S["x"][0]) < 1e-6
