@@ -109,7 +109,10 @@ enum {
   R_GVP = R_GV + 6,        // [6] gradient w.r.t. v_prev
   R_GPH = R_GVP + 6,       // [2] gradient w.r.t. dphi, ddphi (tracking + path-state cost); phi part is in GY
   R_COST = R_GPH + 2,      // [1] stage cost
-  R_SIZE = R_COST + 2
+  R_HYB = R_COST + 2,      // [8][8] y-block (p_pos, p_rot, phi, dphi) of W~: HY + z.HD + J_d^T Sigma_s J_d + dphi tracking term
+  R_GJ1 = R_HYB + 64,      // [8] sum_r JD_r / s_r              (multiplied by mu in g^)
+  R_GJ2 = R_GJ1 + 8,       // [8] sum_r JD_r Sigma_r (d_r + s_r)
+  R_SIZE = R_GJ2 + 8
 };
 // forward-kinematics scratch of one chain evaluation
 enum {

@@ -49,25 +49,22 @@ BMPC_DEV void eval_instance(const Ctx& cx, const Config& C, const Work& W, Smem&
     const KktCoef kc = kkt_coef(C, io.p);
     PAR_FOR(i, n * n) io.hess[i] = 0.0;
     BMPC_SYNC();
+    kkt_build(cx, C, W, kc, 0.0, false);
+    const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
     for (int k = 0; k < N; k++) {
-      PAR_FOR(i, NX * NX) S.M[i] = 0.0;
-      BMPC_SYNC();
-      assemble_diag(cx, C, W, kc, k, 0.0, 0.0, S.M, 2);
-      PAR_FOR(i, NX * NX) { const int a = i / NX, b = i - NX * a; io.hess[(size_t)(NX * k + a) * n + NX * k + b] = S.M[i]; }
+      PAR_FOR(i, NX * NX) { const int a = i / NX, b = i - NX * a; io.hess[(size_t)(NX * k + a) * n + NX * k + b] = W.Wd[(size_t)k * NX * NX + i]; }
       if (k > 0) {
-        build_offdiag(cx, C, W, kc, k, S.OU, S.odv);
-        const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
+        const double* rec = W.rec + (size_t)k * R_SIZE;
         PAR_FOR(i, NX * NX) {
           const int a = i / NX, b = i - NX * a;   // row in w_k, col in w_{k-1}
           double v = 0.0;
-          if (a < 8) v = S.OU[a * NX + b];
+          if (a < 8) v = W.OUa[(size_t)k * NU * NX + a * NX + b];
           else if (a >= oVLIN && a < oVLIN + 6 && b == a) v = ovv;
-          else if (a == oDDPHI && b >= oVLIN && b < oVLIN + 6) v = S.odv[b - oVLIN];
+          else if (a == oDDPHI && b >= oVLIN && b < oVLIN + 6) v = 2 * kc.w5 * rec[R_DPD + b - oVLIN] * kc.idt;
           io.hess[(size_t)(NX * k + a) * n + NX * (k - 1) + b] = v;
           io.hess[(size_t)(NX * (k - 1) + b) * n + NX * k + a] = v;
         }
       }
-      BMPC_SYNC();
     }
   }
   BMPC_SYNC();

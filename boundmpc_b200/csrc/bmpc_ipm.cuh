@@ -126,11 +126,12 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
     if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * fmax(1.0, th_cur); theta_min = 1e-4 * fmax(1.0, th_cur); }
     // ---- search direction with inertia correction
     double dwreg = 0.0;
-    bool ok = kkt_solve(cx, C, W, p, S, mu, 0.0);
+    kkt_build(cx, C, W, kkt_coef(C, p), mu, true);
+    bool ok = kkt_solve(cx, C, W, p, S, 0.0);
     if (!ok) {
       dwreg = delta_w_last == 0.0 ? 1e-4 : fmax(1e-20, delta_w_last / 3);
       for (int tries = 0; tries < 60; tries++) {
-        ok = kkt_solve(cx, C, W, p, S, mu, dwreg);
+        ok = kkt_solve(cx, C, W, p, S, dwreg);
         if (ok) break;
         dwreg *= (delta_w_last == 0.0 ? 100.0 : 8.0);
         if (dwreg > 1e40) break;

@@ -42,12 +42,14 @@ struct Work {
   double *Kk;                                               // [N][8*44]
   double *kap;                                              // [N][8]
   double *cost;                                             // [N]
+  double *Wd;                                               // [N][44*44] diagonal blocks of W~ (without delta_w)
+  double *OUa;                                              // [N][8*44]  rows u_k of the off-diagonal blocks W~_{k,k-1}
   double *wp0;                                              // [44] stage-0 "previous block" built from p
 };
 
 BMPC_HD size_t work_doubles(int N) {
   size_t n = (size_t)NX * N, ne = (size_t)NE * N, nd = (size_t)ND * N;
-  return 9 * n + 4 * ne + 7 * nd + (size_t)N * R_SIZE + (size_t)2 * N * F_SIZE + (size_t)N * 8 * NX + (size_t)N * 8 + N + NX;
+  return 9 * n + 4 * ne + 7 * nd + (size_t)N * R_SIZE + (size_t)2 * N * F_SIZE + (size_t)N * 8 * NX + (size_t)N * 8 + N + NX + (size_t)N * (NX * NX + NU * NX);
 }
 BMPC_DEV void work_carve(Work& W, double* base, int N) {
   size_t n = (size_t)NX * N, ne = (size_t)NE * N, nd = (size_t)ND * N;
@@ -62,6 +64,8 @@ BMPC_DEV void work_carve(Work& W, double* base, int N) {
   W.Kk = q; q += (size_t)N * 8 * NX;
   W.kap = q; q += (size_t)N * 8;
   W.cost = q; q += N;
+  W.Wd = q; q += (size_t)N * NX * NX;
+  W.OUa = q; q += (size_t)N * NU * NX;
   W.wp0 = q; q += NX;
 }
 
@@ -118,15 +122,17 @@ BMPC_DEV void phase_integrate(const Ctx& cx, const Config& C, const Work& W, con
 BMPC_DEV void fk_chain(double* f) {
   double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   double o[3] = {0, 0, 0};
-  double org[7][3];
+  double org[7][3], z[7][3], dq[7];
+#pragma unroll
   for (int k = 0; k < 7; k++) {
     double Rn[3][3];
     for (int i = 0; i < 3; i++) o[i] += R[i][0] * kJXYZ[k][0] + R[i][1] * kJXYZ[k][1] + R[i][2] * kJXYZ[k][2];
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) Rn[i][j] = R[i][0] * kJROT[k][0][j] + R[i][1] * kJROT[k][1][j] + R[i][2] * kJROT[k][2][j];
-    for (int i = 0; i < 3; i++) { f[F_Z + 3 * k + i] = Rn[i][2]; org[k][i] = o[i]; }
+    for (int i = 0; i < 3; i++) { z[k][i] = Rn[i][2]; org[k][i] = o[i]; }
     double sn, cs;
     sincos(f[F_Q + k], &sn, &cs);
+    dq[k] = f[F_DQ + k];
     for (int i = 0; i < 3; i++) {
       R[i][0] = Rn[i][0] * cs + Rn[i][1] * sn;
       R[i][1] = Rn[i][1] * cs - Rn[i][0] * sn;
@@ -135,25 +141,24 @@ BMPC_DEV void fk_chain(double* f) {
   }
   double pos[3];
   for (int i = 0; i < 3; i++) { pos[i] = o[i] + R[i][2] * kTOOLZ; f[F_POS + i] = pos[i]; }
-  for (int k = 0; k < 7; k++)
-    for (int i = 0; i < 3; i++) f[F_R + 3 * k + i] = pos[i] - org[k][i];
   // head sums  OH_i = sum_{k<i} dq_k z_k  (OH_7 = omega)
   double acc[3] = {0, 0, 0};
-  for (int k = 0; k < 7; k++) {
-    for (int i = 0; i < 3; i++) { f[F_OH + 3 * k + i] = acc[i]; acc[i] += f[F_DQ + k] * f[F_Z + 3 * k + i]; }
-  }
+#pragma unroll
+  for (int k = 0; k < 7; k++)
+    for (int i = 0; i < 3; i++) { f[F_Z + 3 * k + i] = z[k][i]; f[F_OH + 3 * k + i] = acc[i]; acc[i] += dq[k] * z[k][i]; }
   for (int i = 0; i < 3; i++) f[F_OH + 21 + i] = acc[i];
   // tail sums  W_i = sum_{k>=i} dq_k z_k x r_k ,  OT_i = sum_{k>i} dq_k z_k
   double wv[3] = {0, 0, 0}, ot[3] = {0, 0, 0};
+#pragma unroll
   for (int k = 6; k >= 0; k--) {
-    double cr[3];
-    cross3(f + F_Z + 3 * k, f + F_R + 3 * k, cr);
-    const double dq = f[F_DQ + k];
+    double r[3], cr[3];
+    for (int i = 0; i < 3; i++) { r[i] = pos[i] - org[k][i]; f[F_R + 3 * k + i] = r[i]; }
+    cross3(z[k], r, cr);
     for (int i = 0; i < 3; i++) {
       f[F_OT + 3 * k + i] = ot[i];
-      wv[i] += dq * cr[i];
+      wv[i] += dq[k] * cr[i];
       f[F_W + 3 * k + i] = wv[i];
-      ot[i] += dq * f[F_Z + 3 * k + i];
+      ot[i] += dq[k] * z[k][i];
     }
   }
 }
@@ -220,7 +225,7 @@ BMPC_DEV void blend_terms(double wgt, const double* a, const double (*A)[7], con
 
 template <int MODE>
 BMPC_DEV void path_stage(const Config& C, const double* p, const double* wp, const double* w, double* rec, double* dout,
-                         double* cost_out, double* gq) {
+                         double* cost_out, double* gq, const double* sk = nullptr, const double* zk = nullptr) {
   const PLayout& L = C.L;
   const int S = L.S;
   const double phi = w[oPHI], dphi = w[oDPHI], ddphi = w[oDDPHI];
@@ -390,6 +395,30 @@ BMPC_DEV void path_stage(const Config& C, const double* p, const double* wp, con
   for (int i = 0; i < 7; i++) rec[R_GY + i] = GY[i];
   for (int i = 0; i < 49; i++) rec[R_HY + i] = HY[i];
   rec[R_COST] = cost;
+  // y-block of the condensed Hessian and the slack part of g^ (Sigma_r = z_r / s_r)
+  {
+    const double* JD = rec + R_JD;
+    double nd = 0.0, zh = 0.0;
+    for (int m = 0; m < 6; m++) nd += dpd[m] * dpd[m];
+    double sig[ND], c1[ND], c2[ND];
+    for (int r = 0; r < ND; r++) {
+      const double sv = sk[r], zv = zk[r];
+      sig[r] = zv / sv; c1[r] = 1.0 / sv; c2[r] = sig[r] * (dout[r] + sv);
+      zh += zv * rec[R_HD + r];
+    }
+    for (int a = 0; a < 8; a++) {
+      double g1 = 0.0, g2 = 0.0;
+      for (int r = 0; r < ND; r++) { g1 += JD[r * 8 + a] * c1[r]; g2 += JD[r * 8 + a] * c2[r]; }
+      rec[R_GJ1 + a] = g1; rec[R_GJ2 + a] = g2;
+      for (int b = 0; b < 8; b++) {
+        double v = (a < 7 && b < 7) ? HY[a * 7 + b] : 0.0;
+        for (int r = 0; r < ND; r++) v += sig[r] * JD[r * 8 + a] * JD[r * 8 + b];
+        if (a == 6 && b == 6) v += zh;
+        if (a == 7 && b == 7) v += 2 * w2 * nd + 2 * w7;
+        rec[R_HYB + a * 8 + b] = v;
+      }
+    }
+  }
   *cost_out = cost;
 }
 
@@ -397,7 +426,7 @@ template <int MODE>
 BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq) {
   PAR_FOR(k, C.N) {
     path_stage<MODE>(C, p, prev_block(W, x, k), x + NX * k, W.rec + (size_t)k * R_SIZE, d + ND * k, W.cost + k,
-                     MODE == 2 ? gq + NQ * k : nullptr);
+                     MODE == 2 ? gq + NQ * k : nullptr, W.s + ND * k, W.zs + ND * k);
   }
 }
 

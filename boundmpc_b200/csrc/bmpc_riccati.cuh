@@ -57,116 +57,128 @@ BMPC_DEV void type_coef(const Config& C, double* al, double* be, int* off) {
   off[0] = oU; off[1] = oQ; off[2] = oDQ; off[3] = oDDQ; off[4] = oU;
 }
 
-// M += W~_kk : Lagrangian Hessian diagonal block of stage k, bound / slack barrier terms, delta_w.
-// Also writes g^_k (gradient of the barrier problem without the equality multipliers) into gh.
-// M must hold P_{k+1} (or zero) on entry.  All threads; ends with a sync.
-BMPC_DEV void assemble_diag(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, int k, double mu, double delta_w,
-                            double* M, int mode) {
-  // mode 0: barrier terms + write g^ ; 1: barrier terms ; 2: pure Lagrangian Hessian (tests)
-  const bool with_gh = mode == 0, barrier = mode != 2;
+// joint-variable classification of a stage index: type 0 = u (previous input when seen from the next
+// stage), 1 = q, 2 = dq, 3 = ddq; -1 otherwise
+BMPC_DEV int jtype(int a) { return a < 7 ? 0 : (a < 8 ? -1 : (a < 15 ? 1 : (a < 22 ? 2 : (a < 29 ? 3 : -1)))); }
+BMPC_DEV int jidx(int a) { return a < 7 ? a : (a < 15 ? a - 8 : (a < 22 ? a - 15 : a - 22)); }
+BMPC_DEV int yidx(int a) { return (a >= oPPOS && a < oPPOS + 6) ? a - oPPOS : (a == oPHI ? 6 : (a == oDPHI ? 7 : -1)); }
+
+// One entry (a, b) of the diagonal block W~_kk (gather form: every entry is written by exactly one
+// thread).  barrier = true adds the bound terms and uses the y-block with the slack terms.
+BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, const double* al, const double* be, int k, int a, int b,
+                         bool barrier) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
-  const double* recn = rec + R_SIZE;
   const bool has_next = k + 1 < C.N;
-  double al[5], be[5]; int off[5];
-  type_coef(C, al, be, off);
-  double nd = 0.0;
-  for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
-  // (a) diagonal: separable cost, tracking terms, bounds, regularisation; gradient part of g^
-  PAR_FOR(i, NX) {
-    const int gi = NX * k + i;
-    double dg = delta_w, gb = W.gradf[gi];
-    if (i < 7) dg += 2 * kc.w13; else if (i == 7) dg += 2 * kc.w9; else if (i < 15) dg += 2 * kc.w10;
-    else if (i < 22) dg += 2 * kc.w11; else if (i < 29) dg += 2 * kc.w12;
-    else if (i >= oVLIN && i < oVLIN + 6) dg += 2 * kc.w2 + 2 * kc.w5 * kc.idt * kc.idt * (has_next ? 2.0 : 1.0);
-    else if (i == oDDPHI) dg += 2 * kc.w5 * nd + 2 * kc.w8;
-    const double lb = C.lb[i], ub = C.ub[i];
-    if (barrier && lb > -1e300) { const double sl = W.x[gi] - lb; dg += W.zL[gi] / sl; gb -= mu / sl; }
-    if (barrier && ub < 1e300) { const double su = ub - W.x[gi]; dg += W.zU[gi] / su; gb += mu / su; }
-    M[i * NX + i] += dg;
-    if (with_gh) W.gh[gi] = gb;
-  }
-  BMPC_SYNC();
-  // (b) y-block (p_pos, p_rot, phi) + dphi: cost Hessian, inequality curvature, J_d^T Sigma J_d
-  PAR_FOR(it, 64) {
-    const int a = it >> 3, b = it & 7;
-    const int ia = a < 6 ? oPPOS + a : (a == 6 ? oPHI : oDPHI);
-    const int ib = b < 6 ? oPPOS + b : (b == 6 ? oPHI : oDPHI);
-    double v = 0.0;
-    if (a < 7 && b < 7) v = rec[R_HY + a * 7 + b];
-    if (a == 7 && b == 7) v = 2 * kc.w2 * nd + 2 * kc.w7;
-    const double* JD = rec + R_JD;
-    for (int r = 0; r < ND; r++) {
-      const double sv = W.s[ND * k + r], zv = W.zs[ND * k + r];
-      if (barrier) v += (zv / sv) * JD[r * 8 + a] * JD[r * 8 + b];
-      if (a == 6 && b == 6) v += zv * rec[R_HD + r];
+  double v = 0.0;
+  if (a == b) {
+    if (a < 7) v = 2 * kc.w13; else if (a == 7) v = 2 * kc.w9; else if (a < 15) v = 2 * kc.w10;
+    else if (a < 22) v = 2 * kc.w11; else if (a < 29) v = 2 * kc.w12;
+    else if (a >= oVLIN && a < oVLIN + 6) v = 2 * kc.w2 + 2 * kc.w5 * kc.idt * kc.idt * (has_next ? 2.0 : 1.0);
+    else if (a == oDDPHI) {
+      double nd = 0.0;
+      for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+      v = 2 * kc.w5 * nd + 2 * kc.w8;
     }
-    M[ia * NX + ib] += v;
-    if (with_gh && b == 0) {   // g^ += J_d^T (mu / s + Sigma_s (d + s))
-      double gsum = 0.0;
-      for (int r = 0; r < ND; r++) {
-        const double sv = W.s[ND * k + r], zv = W.zs[ND * k + r];
-        gsum += JD[r * 8 + a] * (mu / sv + (zv / sv) * (W.d[ND * k + r] + sv));
+    if (barrier) {
+      const int gi = NX * k + a;
+      const double lb = C.lb[a], ub = C.ub[a];
+      if (lb > -1e300) v += W.zL[gi] / (W.x[gi] - lb);
+      if (ub < 1e300) v += W.zU[gi] / (ub - W.x[gi]);
+    }
+  }
+  const int ya = yidx(a), yb = yidx(b);
+  if (ya >= 0 && yb >= 0) {
+    if (barrier) v += rec[R_HYB + ya * 8 + yb];
+    else {
+      if (ya < 7 && yb < 7) v += rec[R_HY + ya * 7 + yb];
+      if (ya == 6 && yb == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * rec[R_HD + r];
+      if (ya == 7 && yb == 7) {
+        double nd = 0.0;
+        for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+        v += 2 * kc.w2 * nd + 2 * kc.w7;
       }
-      W.gh[NX * k + ia] += gsum;
     }
   }
-  //     velocity / acceleration tracking cross terms (v(6) x dphi, v(6) x ddphi)
-  PAR_FOR(m, 6) {
-    const double dp = rec[R_DPD + m];
-    M[(oVLIN + m) * NX + oDPHI] += -2 * kc.w2 * dp;
-    M[oDPHI * NX + oVLIN + m] += -2 * kc.w2 * dp;
-    M[(oVLIN + m) * NX + oDDPHI] += -2 * kc.w5 * dp * kc.idt;
-    M[oDDPHI * NX + oVLIN + m] += -2 * kc.w5 * dp * kc.idt;
+  // velocity / acceleration tracking cross terms
+  {
+    const int va = (a >= oVLIN && a < oVLIN + 6) ? a - oVLIN : -1, vb = (b >= oVLIN && b < oVLIN + 6) ? b - oVLIN : -1;
+    if (va >= 0 && b == oDPHI) v += -2 * kc.w2 * rec[R_DPD + va];
+    if (vb >= 0 && a == oDPHI) v += -2 * kc.w2 * rec[R_DPD + vb];
+    if (va >= 0 && b == oDDPHI) v += -2 * kc.w5 * rec[R_DPD + va] * kc.idt;
+    if (vb >= 0 && a == oDDPHI) v += -2 * kc.w5 * rec[R_DPD + vb] * kc.idt;
   }
-  //     kinematic curvature u_k x u_k of this stage
-  PAR_FOR(ij, 49) {
-    const int i = ij / 7, j = ij - 7 * i;
-    const double hqq = rec[R_HQQN + ij], hqd = rec[R_HQDN + ij], hdq = rec[R_HQDN + j * 7 + i];
-    M[(oU + i) * NX + oU + j] += al[4] * al[4] * hqq + al[4] * be[4] * (hqd + hdq);
-  }
-  BMPC_SYNC();
-  // (c) kinematic curvature (um,q,dq,ddq)^2 contributed by the next stage's constraints
-  if (has_next) {
-    PAR_FOR(it, 16 * 49) {
-      const int st = it / 49, ij = it - 49 * st, s = st >> 2, t = st & 3, i = ij / 7, j = ij - 7 * i;
-      const double hqq = recn[R_HQQN + ij], hqd = recn[R_HQDN + ij], hdq = recn[R_HQDN + j * 7 + i];
-      double v = al[s] * al[t] * hqq + al[s] * be[t] * hqd + be[s] * al[t] * hdq;
-      if (s == 1 && t == 1) v += recn[R_HQQK + ij];
-      if (s == 1 && t == 2) v += recn[R_HQDK + ij];
-      if (s == 2 && t == 1) v += recn[R_HQDK + j * 7 + i];
-      M[(off[s] + i) * NX + off[t] + j] += v;
+  // kinematic curvature
+  const int sa = jtype(a), sb = jtype(b);
+  if (sa >= 0 && sb >= 0) {
+    const int i = jidx(a), j = jidx(b);
+    if (sa == 0 && sb == 0) {
+      const double hqq = rec[R_HQQN + i * 7 + j], hqd = rec[R_HQDN + i * 7 + j], hdq = rec[R_HQDN + j * 7 + i];
+      v += al[4] * al[4] * hqq + al[4] * be[4] * (hqd + hdq);
+    }
+    if (has_next) {
+      const double* rn = rec + R_SIZE;
+      const double hqq = rn[R_HQQN + i * 7 + j], hqd = rn[R_HQDN + i * 7 + j], hdq = rn[R_HQDN + j * 7 + i];
+      v += al[sa] * al[sb] * hqq + al[sa] * be[sb] * hqd + be[sa] * al[sb] * hdq;
+      if (sa == 1 && sb == 1) v += rn[R_HQQK + i * 7 + j];
+      if (sa == 1 && sb == 2) v += rn[R_HQDK + i * 7 + j];
+      if (sa == 2 && sb == 1) v += rn[R_HQDK + j * 7 + i];
     }
   }
-  BMPC_SYNC();
+  return v;
 }
 
-// OU = rows u_k of W~_{k,k-1} (kinematic coupling of u_k with (um,q,dq,ddq) of the previous block);
-// odv[m] = d2/(d ddphi_{k+1} d v_k[m]).  The v_{k+1} x v_k entries are the constant -2 w5 / dt^2.
-BMPC_DEV void build_offdiag(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, int k, double* OU, double* odv) {
+// entry (i, col) of the rows u_k of W~_{k,k-1} (kinematic coupling of u_k with (um, q, dq, ddq) of the previous block)
+BMPC_DEV double ou_entry(const Work& W, const double* al, const double* be, int k, int i, int col) {
+  const int t = jtype(col);
+  if (i >= 7 || t < 0) return 0.0;
   const double* rec = W.rec + (size_t)k * R_SIZE;
+  const int j = jidx(col);
+  return al[4] * al[t] * rec[R_HQQN + i * 7 + j] + al[4] * be[t] * rec[R_HQDN + i * 7 + j] + be[4] * al[t] * rec[R_HQDN + j * 7 + i];
+}
+
+// All stages at once: W.Wd, W.OUa and g^ (gradient of the barrier problem without the equality multipliers)
+BMPC_DEV void kkt_build(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, double mu, bool barrier) {
   double al[5], be[5]; int off[5];
   type_coef(C, al, be, off);
-  PAR_FOR(i, NU * NX) OU[i] = 0.0;
-  BMPC_SYNC();
-  PAR_FOR(it, 4 * 49) {
-    const int t = it / 49, ij = it - 49 * t, i = ij / 7, j = ij - 7 * i;
-    const double hqq = rec[R_HQQN + ij], hqd = rec[R_HQDN + ij], hdq = rec[R_HQDN + j * 7 + i];
-    OU[i * NX + off[t] + j] = al[4] * al[t] * hqq + al[4] * be[t] * hqd + be[4] * al[t] * hdq;
+  const int N = C.N;
+  PAR_FOR(it, N * NX * NX) {
+    const int k = it / (NX * NX), ab = it - k * NX * NX, a = ab / NX, b = ab - NX * a;
+    W.Wd[it] = wd_entry(C, W, kc, al, be, k, a, b, barrier);
   }
-  PAR_FOR(m, 6) odv[m] = 2 * kc.w5 * rec[R_DPD + m] * kc.idt;
+  PAR_FOR(it, N * NU * NX) {
+    const int k = it / (NU * NX), ic = it - k * NU * NX, i = ic / NX, col = ic - NX * i;
+    W.OUa[it] = k > 0 ? ou_entry(W, al, be, k, i, col) : 0.0;
+  }
+  if (barrier) {
+    PAR_FOR(gi, C.n) {
+      const int k = gi / NX, a = gi - NX * k;
+      double gb = W.gradf[gi];
+      const double lb = C.lb[a], ub = C.ub[a];
+      if (lb > -1e300) gb -= mu / (W.x[gi] - lb);
+      if (ub < 1e300) gb += mu / (ub - W.x[gi]);
+      const int ya = yidx(a);
+      if (ya >= 0) { const double* rec = W.rec + (size_t)k * R_SIZE; gb += mu * rec[R_GJ1 + ya] + rec[R_GJ2 + ya]; }
+      W.gh[gi] = gb;
+    }
+  }
   BMPC_SYNC();
 }
 
 // One backward Riccati step for stage k.  On entry S.M = P_{k+1} (zero for k = N-1), S.pv = p_{k+1}.
 // On exit S.M = P_k, S.pv = p_k, gains stored in W.Kk / W.kap.  Returns false if Q_uu is not PD.
-BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double mu, double delta_w) {
-  assemble_diag(cx, C, W, kc, k, mu, delta_w, S.M, 0);
+BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
   const double* c = W.c + NE * k;
+  const double* Wd = W.Wd + (size_t)k * NX * NX;
+  PAR_FOR(i, NX * NX) S.M[i] += Wd[i] + ((i % (NX + 1)) == 0 ? delta_w : 0.0);
   PAR_FOR(i, NK * NZ) S.GK[i] = rec[R_GK + i];
   PAR_FOR(i, NX) S.mv[i] = W.gh[NX * k + i] + S.pv[i];
-  if (k > 0) build_offdiag(cx, C, W, kc, k, S.OU, S.odv);
-  else BMPC_SYNC();
+  if (k > 0) {
+    const double* OUa = W.OUa + (size_t)k * NU * NX;
+    PAR_FOR(i, NU * NX) S.OU[i] = OUa[i];
+    PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * rec[R_DPD + m] * kc.idt;
+  }
+  BMPC_SYNC();
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
   const int ncol = k > 0 ? NZ : NU;          // stage 0: the previous block is fixed -> only the u-columns
   const int c0 = k > 0 ? 0 : NX;
@@ -204,23 +216,18 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     if (b >= NX) v += S.Z[(b - NX) * NZ + a];
     if (a >= NX && b >= NX) v += S.M[(a - NX) * NX + (b - NX)];
     if (k > 0) {
-      // EO[a][b] = (E^T O)[a][b] for b < 44; contributes at (a,b) and, for a < 44, EO[b][a] at (a,b)
-      // O_x: rows v_{k+1} (x-rows 27..32) <- cols v_k (35..40): ovv on the diagonal; row ddphi (35) <- odv
-      if (b < NX) {
-        if (a >= NX) v += S.OU[(a - NX) * NX + b];
-        if (b >= oVLIN && b < oVLIN + 6) {
-          const int m = b - oVLIN;
-          double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : (a == NX + oUPHI ? C.c_u : 0.0));
-          v += S.GK[(6 + m) * NZ + a] * ovv + g35 * S.odv[m];
-        }
+      // EO = E^T O (52 x 44): contributes EO[a][b] for b < 44 and EO[b][a] for a < 44.
+      // O_x: rows v_{k+1} (x-rows 27..32) x cols v_k (35..40): ovv on the diagonal; row ddphi (x-row 35): odv
+      if (b < NX && b >= oVLIN && b < oVLIN + 6) {
+        const int m = b - oVLIN;
+        const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : (a == NX + oUPHI ? C.c_u : 0.0));
+        v += S.GK[(6 + m) * NZ + a] * ovv + g35 * S.odv[m];
       }
       if (a < NX) {
-        if (b >= NX) { /* EO[b][a] with b >= 44 handled above by symmetry of the (a>=NX) branch: here a < NX so add it */
-          v += S.OU[(b - NX) * NX + a];
-        }
+        if (b >= NX) v += S.OU[(b - NX) * NX + a];
         if (a >= oVLIN && a < oVLIN + 6) {
           const int m = a - oVLIN;
-          double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : (b == NX + oUPHI ? C.c_u : 0.0));
+          const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : (b == NX + oUPHI ? C.c_u : 0.0));
           v += S.GK[(6 + m) * NZ + b] * ovv + g35 * S.odv[m];
         }
       }
@@ -236,18 +243,34 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     S.qv[a] = v;
   }
   BMPC_SYNC();
-  // Cholesky of Q_uu (8 x 8) by one thread; failure flag broadcast through shared memory
+  // Cholesky of Q_uu (8 x 8) in registers by one thread; Lc holds L with the RECIPROCAL diagonal
   if (cx.tid == 0) {
+    double A[NU][NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) A[i][j] = S.Q[(NX + j) * NZ + NX + i];
     int ok = 1;
-    for (int i = 0; i < NU && ok; i++)
-      for (int j = 0; j <= i; j++) {
-        double a = S.Q[(NX + j) * NZ + NX + i];
-        for (int l = 0; l < j; l++) a -= S.Lc[i * NU + l] * S.Lc[j * NU + l];
-        if (i == j) {
-          if (!(a > 1e-14)) { ok = 0; break; }
-          S.Lc[i * NU + i] = sqrt(a);
-        } else S.Lc[i * NU + j] = a / S.Lc[j * NU + j];
+#pragma unroll
+    for (int j = 0; j < NU; j++) {
+      double d = A[j][j];
+#pragma unroll
+      for (int l = 0; l < j; l++) d -= A[j][l] * A[j][l];
+      if (!(d > 1e-14)) ok = 0;
+      const double inv = 1.0 / sqrt(d > 1e-14 ? d : 1.0);
+      A[j][j] = inv;
+#pragma unroll
+      for (int i = j + 1; i < NU; i++) {
+        double e = A[i][j];
+#pragma unroll
+        for (int l = 0; l < j; l++) e -= A[i][l] * A[j][l];
+        A[i][j] = e * inv;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < NU; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) S.Lc[i * NU + j] = A[i][j];
     S.flag[0] = ok;
   }
   BMPC_SYNC();
@@ -257,10 +280,28 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
   double* kap = W.kap + k * NU;
   PAR_FOR(col, (k > 0 ? NX : 0) + 1) {
     const bool isk = col == (k > 0 ? NX : 0);
-    double bcol[NU];
+    double L[NU][NU], bcol[NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) L[i][j] = S.Lc[i * NU + j];
+#pragma unroll
     for (int i = 0; i < NU; i++) bcol[i] = isk ? -S.qv[NX + i] : -S.Q[col * NZ + NX + i];
-    for (int i = 0; i < NU; i++) { double a = bcol[i]; for (int l = 0; l < i; l++) a -= S.Lc[i * NU + l] * bcol[l]; bcol[i] = a / S.Lc[i * NU + i]; }
-    for (int i = NU - 1; i >= 0; i--) { double a = bcol[i]; for (int l = i + 1; l < NU; l++) a -= S.Lc[l * NU + i] * bcol[l]; bcol[i] = a / S.Lc[i * NU + i]; }
+#pragma unroll
+    for (int i = 0; i < NU; i++) {
+      double a = bcol[i];
+#pragma unroll
+      for (int l = 0; l < i; l++) a -= L[i][l] * bcol[l];
+      bcol[i] = a * L[i][i];
+    }
+#pragma unroll
+    for (int i = NU - 1; i >= 0; i--) {
+      double a = bcol[i];
+#pragma unroll
+      for (int l = i + 1; l < NU; l++) a -= L[l][i] * bcol[l];
+      bcol[i] = a * L[i][i];
+    }
+#pragma unroll
     for (int i = 0; i < NU; i++) { if (isk) kap[i] = bcol[i]; else K[i * NX + col] = bcol[i]; }
   }
   BMPC_SYNC();
@@ -270,6 +311,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     const int a = it / NX, b = it - NX * a;
     if (a > b) continue;
     double v = S.Q[a * NZ + b];
+#pragma unroll
     for (int i = 0; i < NU; i++) v += S.Q[a * NZ + NX + i] * K[i * NX + b];
     S.M[a * NX + b] = v;
     S.M[b * NX + a] = v;
@@ -283,14 +325,15 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
   return true;
 }
 
-// Full KKT solve: dx (primal step) and ynew (equality multipliers of the full step).
-BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double mu, double delta_w) {
+// Backward + forward + adjoint sweeps on the blocks prepared by kkt_build:
+// dx (primal step) and ynew (equality multipliers of the full step).
+BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
   const KktCoef kc = kkt_coef(C, p);
   PAR_FOR(i, NX * NX) S.M[i] = 0.0;
   PAR_FOR(i, NX) S.pv[i] = 0.0;
   BMPC_SYNC();
   for (int k = C.N - 1; k >= 0; k--)
-    if (!riccati_stage(cx, C, W, kc, S, k, mu, delta_w)) return false;
+    if (!riccati_stage(cx, C, W, kc, S, k, delta_w)) return false;
   // forward sweep
   for (int k = 0; k < C.N; k++) {
     const double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
@@ -310,11 +353,9 @@ BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const dou
   //   y_k = [W~_kk dw_k + O_k dw_{k-1} + O_{k+1}^T dw_{k+1} + g^_k]_x + [A_hat_{k+1}^T y_{k+1}]_x
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
   for (int k = C.N - 1; k >= 0; k--) {
-    PAR_FOR(i, NX * NX) S.M[i] = 0.0;
-    BMPC_SYNC();
-    assemble_diag(cx, C, W, kc, k, mu, delta_w, S.M, 1);
     const bool has_next = k + 1 < C.N;
-    if (has_next) build_offdiag(cx, C, W, kc, k + 1, S.OU, S.odv);   // O_{k+1}
+    const double* Wd = W.Wd + (size_t)k * NX * NX;
+    const double* OUn = W.OUa + (size_t)(k + 1) * NU * NX;
     const double* dw = W.dx + NX * k;
     const double* dwp = k > 0 ? W.dx + NX * (k - 1) : nullptr;
     const double* dwn = has_next ? W.dx + NX * (k + 1) : nullptr;
@@ -322,15 +363,15 @@ BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const dou
     const double* reck = W.rec + (size_t)k * R_SIZE;
     PAR_FOR(i, NE) {
       const int r = 8 + i;
-      double a = W.gh[NX * k + r];
-      for (int j = 0; j < NX; j++) a += S.M[r * NX + j] * dw[j];
+      double a = W.gh[NX * k + r] + delta_w * dw[r];
+      for (int j = 0; j < NX; j++) a += Wd[r * NX + j] * dw[j];
       if (dwp) {   // O_k rows v, ddphi
         if (r >= oVLIN && r < oVLIN + 6) a += ovv * dwp[r];
         if (r == oDDPHI) for (int m = 0; m < 6; m++) a += 2 * kc.w5 * reck[R_DPD + m] * kc.idt * dwp[oVLIN + m];
       }
       if (has_next) {
-        for (int q = 0; q < 7; q++) a += S.OU[q * NX + r] * dwn[q];                     // O_u,k+1^T du_{k+1}
-        if (r >= oVLIN && r < oVLIN + 6) a += ovv * dwn[r] + S.odv[r - oVLIN] * dwn[oDDPHI];   // O_x,k+1^T dx_{k+2}
+        for (int q = 0; q < 7; q++) a += OUn[q * NX + r] * dwn[q];                                   // O_u,k+1^T du_{k+1}
+        if (r >= oVLIN && r < oVLIN + 6) a += ovv * dwn[r] + 2 * kc.w5 * reck[R_SIZE + R_DPD + (r - oVLIN)] * kc.idt * dwn[oDDPHI];
         a += GT_vec(C, GKn, W.ynew + NE * (k + 1), r);
       }
       W.ynew[NE * k + i] = a;
