@@ -5,7 +5,9 @@ An instance is one solver call `(x0, p)` as the reference's `BoundMPC.step` woul
 scenario (bound_mpc_node.py:292-372: step -> integrate_joint -> next state) with the CUDA solver,
 snapshotting the controller state at every step, and (2) for instance i restoring the snapshot of
 step `i mod T`, perturbing the joint state with `default_rng(20261017 + i)` and calling the
-host-side `prepare()`.  Odd instances use the cold start, even ones the shifted warm start.
+host-side `prepare()`.  As in the reference, the cold start (BoundMPC.py:316-321) is used by the instances
+drawn from step 0 only (its all-zero path parameter is meaningless further along the path); all
+others use the shifted previous solution (BoundMPC.py:373-375).
 Generated batches are cached as .npz (inputs are never part of a timed region).
 """
 import copy
@@ -75,30 +77,78 @@ def nominal_sequence(scn, solver, max_steps=600, record=None):
     return snaps, stats, x_phi_d
 
 
-def perturbed_instance(mpc, snaps, x_phi_d, i, bound_scale=False):
-    """Instance i of a batch."""
+# perturbation of the joint state (standard deviations at scale 1): sensor-noise sized.  The
+# error bounds of the scenarios are as tight as 1e-4 m (exp2, middle segment) and the first
+# horizon nodes cannot be moved by the jerk input (h^3/24 * 35 = 1.5e-3 rad), so a perturbed
+# start can make the NLP infeasible; `make_batch` halves the perturbation of such an instance
+# until its zero-jerk roll-out is no further outside the bounds than the unperturbed one.
+SIGMA_Q, SIGMA_DQ, SIGMA_DDQ = 5e-3, 2e-2, 5e-2
+SCALES = (1.0, 0.5, 0.25, 0.125, 0.0625, 0.0)
+CHECK_STAGES = 3
+
+
+def perturbed_instance(mpc, snaps, x_phi_d, i, bound_scale=False, scale=1.0):
+    """Instance i of a batch with the perturbation multiplied by `scale`.
+    Returns the warm start, the parameter vector and the zero-jerk roll-out used as
+    feasibility probe."""
     rng = np.random.default_rng(SEED0 + i)
     snap, st = snaps[i % len(snaps)]
     _restore(mpc, snap)
-    q = st['q'] + rng.normal(0.0, 0.02, 7)
-    dq = st['dq'] + rng.normal(0.0, 0.02, 7)
-    ddq = st['ddq'] + rng.normal(0.0, 0.05, 7)
-    q = np.clip(q, Q_LIM_LOWER + 0.05, Q_LIM_UPPER - 0.05)
-    dq = np.clip(dq, DQ_LIM_LOWER + 0.05, DQ_LIM_UPPER - 0.05)
+    nq, ndq, nddq = rng.normal(0.0, SIGMA_Q, 7), rng.normal(0.0, SIGMA_DQ, 7), rng.normal(0.0, SIGMA_DDQ, 7)
+    q = np.clip(st['q'] + scale * nq, Q_LIM_LOWER + 0.05, Q_LIM_UPPER - 0.05)
+    dq = np.clip(st['dq'] + scale * ndq, DQ_LIM_LOWER + 0.05, DQ_LIM_UPPER - 0.05)
+    ddq = st['ddq'] + scale * nddq
     if bound_scale:
-        f = rng.uniform(0.75, 1.25, 4)
+        # widths x U(1, 1.25): enlarging e_min / e_max enlarges the quartic bound everywhere, so
+        # the nominal closed-loop state stays feasible (shrinking them would not)
+        f = rng.uniform(1.0, 1.25, 4)
         rp = mpc.ref_path
         rp.e_p_min = [v * f[0] for v in rp.e_p_min]
         rp.e_p_max = [v * f[1] for v in rp.e_p_max]
         rp.e_r_min = [v * f[2] for v in rp.e_r_min]
         rp.e_r_max = [v * f[3] for v in rp.e_r_max]
-    if i % 2 == 1:
-        mpc.prev_solution = None
     rm = mpc.robot_model
     p0 = rm.fk(q)
     v0 = rm.jacobian_fk(q) @ dq
     w0, p, _ = mpc.prepare(q, dq, ddq, p0, v0, x_phi_d, st['jerk'])
-    return w0, p
+    return w0, p, _rollout(rm, w0, p, mpc.dt, CHECK_STAGES)
+
+
+def _rollout(rm, w0, p, h, stages):
+    """w0 with its first `stages` nodes replaced by the zero-jerk continuation of the initial
+    state in p (dynamics of SURVEY App. A.4): every equality row of those nodes is zero, so
+    their inequality rows say whether the start itself is inside the error bounds."""
+    x = np.array(w0, float).reshape(-1, 44).copy()
+    q, dq, ddq = p[0:7].copy(), p[7:14].copy(), p[14:21].copy()
+    phi, dphi, ddphi = p[21:24]
+    um = p[81:89].copy()
+    prot = p[27:30].copy()
+    for k in range(stages):
+        om0 = np.ravel(rm.omega_ee(q, dq))
+        qn = q + h * dq + h * h / 2 * ddq + h ** 3 / 8 * um[:7]
+        dqn = dq + h * ddq + h * h / 3 * um[:7]
+        ddqn = ddq + h / 2 * um[:7]
+        phin = phi + h * dphi + h * h / 2 * ddphi + h ** 3 / 8 * um[7]
+        dphin = dphi + h * ddphi + h * h / 3 * um[7]
+        ddphin = ddphi + h / 2 * um[7]
+        om1 = np.ravel(rm.omega_ee(qn, dqn))
+        prot = prot + h / 2 * (om0 + om1)
+        x[k, 0:8] = 0.0
+        x[k, 8:15], x[k, 15:22], x[k, 22:29] = qn, dqn, ddqn
+        x[k, 29:32], x[k, 32:35] = np.ravel(rm.fk_pos(qn)), prot
+        x[k, 35:38], x[k, 38:41] = np.ravel(rm.velocity_ee(qn, dqn)), om1
+        x[k, 41:44] = phin, dphin, ddphin
+        q, dq, ddq, phi, dphi, ddphi, um = qn, dqn, ddqn, phin, dphin, ddphin, np.zeros(8)
+    return x.ravel()
+
+
+def bound_excess(d, N, stages=CHECK_STAGES):
+    """max over the first nodes and the five interval pairs of (|m| - h) / h from the interval-form
+    rows d [B, 12 N] of `eval_batch` (pairs (m - h, -m - h) at columns 2.. of every node)."""
+    d = np.asarray(d).reshape(len(d), N, 12)[:, :stages, 2:].reshape(len(d), stages, 5, 2)
+    h = -0.5 * (d[..., 0] + d[..., 1])
+    m = 0.5 * (d[..., 0] - d[..., 1])
+    return ((np.abs(m) - h) / h).reshape(len(d), -1).max(axis=1)
 
 
 def _cache_path(key):
@@ -106,27 +156,86 @@ def _cache_path(key):
     return os.path.join(CACHE_DIR, hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
 
 
-def make_batch(solver, scenario_names, first, count, n=10, tight=False, bound_scale=False, cache=True):
+class _BoundsOnly:
+    """What BoundMPC.__init__ needs from a solver handle; lets generator workers build
+    controller objects without touching CUDA."""
+
+    def __init__(self, bounds):
+        self._b = bounds
+
+    def bounds(self):
+        return self._b
+
+
+_GEN = {}
+
+
+def _gen_init(seqs, bounds, bound_scale):
+    _GEN['b'] = bound_scale
+    _GEN['seqs'] = {name: (make_mpc(scn, _BoundsOnly(bounds)), snaps, xd) for name, (scn, snaps, xd) in seqs.items()}
+
+
+def _gen_one(job):
+    i, name, scale = job
+    mpc, snaps, xd = _GEN['seqs'][name]
+    return perturbed_instance(mpc, snaps, xd, i, _GEN['b'], scale)
+
+
+def make_batch(solver, scenario_names, first, count, n=10, tight=False, bound_scale=False, cache=True, workers=None,
+               return_scales=False):
     """Instances `first .. first+count-1`; instance i uses scenario_names[i % len(scenario_names)]."""
-    key = f"v3|{scenario_names}|{first}|{count}|{n}|{tight}|{bound_scale}"
+    key = f"v6|{scenario_names}|{first}|{count}|{n}|{tight}|{bound_scale}|{SIGMA_Q}|{SIGMA_DQ}|{SIGMA_DDQ}"
     path = _cache_path(key)
     if cache and os.path.exists(path):
         z = np.load(path)
-        return z['x0'], z['p']
+        return (z['x0'], z['p'], z['scale']) if return_scales else (z['x0'], z['p'])
     seqs = {}
-    for name in set(scenario_names):
+    for name in sorted(set(scenario_names)):
         scn = scenarios.experiment1(n=n, tight=tight) if name == 'exp1' else scenarios.experiment2(n=n)
         snaps, stats, xd = nominal_sequence(scn, solver)
-        seqs[name] = (make_mpc(scn, solver), snaps, xd)
+        seqs[name] = (scn, snaps, xd)
+    bounds = solver.bounds()
+    ids = np.arange(first, first + count)
+    names = [scenario_names[i % len(scenario_names)] for i in ids]
     x0 = np.empty((count, 44 * n))
     p = np.empty((count, solver.np))
-    for j in range(count):
-        i = first + j
-        mpc, snaps, xd = seqs[scenario_names[i % len(scenario_names)]]
-        x0[j], p[j] = perturbed_instance(mpc, snaps, xd, i, bound_scale)
+    used = np.full(count, -1.0)
+    if workers is None:
+        workers = min(16, os.cpu_count() or 1)
+    pool = None
+    if workers > 1 and count >= 64:
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(workers, initializer=_gen_init, initargs=(seqs, bounds, bound_scale))
+        run = lambda jobs: pool.map(_gen_one, jobs, chunksize=max(1, len(jobs) // (workers * 8)))
+    else:
+        _gen_init(seqs, bounds, bound_scale)
+        run = lambda jobs: [_gen_one(j) for j in jobs]
+    try:
+        def excess(jobs):
+            res = run(jobs)
+            xr = np.stack([r[2] for r in res])
+            pp = np.stack([r[1] for r in res])
+            return res, bound_excess(solver.eval_batch(xr, pp, want_jac=False, want_hess=False)["d"], n)
+        # unperturbed instances: the level of bound excess the closed loop itself lives with
+        _, ex0 = excess([(int(i), nm, 0.0) for i, nm in zip(ids, names)])
+        limit = np.maximum(ex0, -0.02)
+        pending = np.arange(count)
+        for scale in SCALES:
+            if len(pending) == 0:
+                break
+            res, ex = excess([(int(ids[j]), names[j], scale) for j in pending])
+            ok = (ex <= limit[pending]) | (scale == 0.0)
+            for j, r, o in zip(pending, res, ok):
+                if o:
+                    x0[j], p[j], used[j] = r[0], r[1], scale
+            pending = pending[~ok]
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     if cache:
-        np.savez(path, x0=x0, p=p)
-    return x0, p
+        np.savez(path, x0=x0, p=p, scale=used)
+    return (x0, p, used) if return_scales else (x0, p)
 
 
 # BASELINE.json configs -> generator arguments

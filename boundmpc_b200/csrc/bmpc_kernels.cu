@@ -65,6 +65,43 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant
   }
 }
 
+// FP64 pipe peak probes (roofline denominator).  Each thread runs 8 independent
+// dependency chains so the DFMA / DMMA pipe is the only limiter.
+__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double m = 1.0 - 1e-12, c = 1e-13;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double* out, int iters) {
+  double acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[i][0]), "+d"(acc[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) s += acc[i][0] + acc[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, const char* a = "") {
@@ -88,6 +125,14 @@ struct bmpc_handle {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int ensure_dbuf(bmpc_handle* h, size_t bytes) {
+  if (h->dbuf_bytes >= bytes) return BMPC_OK;
+  if (h->dbuf) { cudaFree(h->dbuf); h->dbuf = nullptr; h->dbuf_bytes = 0; }
+  CU(cudaMalloc(&h->dbuf, bytes));
+  h->dbuf_bytes = bytes;
+  return BMPC_OK;
+}
 
 static int grid_for(const bmpc_handle* h, int batch) {
   int g = h->sms * h->ctas_per_sm;
@@ -163,6 +208,35 @@ int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes) {
 
 int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 
+int bmpc_fp64_peak(bmpc_handle* h, int32_t kind, double* flops_per_s) {
+  if (!h || !flops_per_s || kind < 0 || kind > 1) return fail(BMPC_E_INVALID, "bmpc_fp64_peak: invalid argument");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_dbuf(h, 256);
+  if (rc) return rc;
+  const int iters = 4096, grid = h->sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(e0, h->stream));
+    if (kind == 0) k_peak_dfma<<<grid, threads, 0, h->stream>>>((double*)h->dbuf, iters);
+    else k_peak_dmma<<<grid, threads, 0, h->stream>>>((double*)h->dbuf, iters);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    // DFMA: 2 flop x 64 per loop trip per thread; DMMA m8n8k4: 2*8*8*4 = 512 flop per warp instruction, 32 per trip per warp
+    const double fl = kind == 0 ? 2.0 * 64 * iters * (double)grid * threads : 512.0 * 32 * iters * (double)grid * (threads / 32);
+    if (rep > 0 && fl / (ms * 1e-3) > best) best = fl / (ms * 1e-3);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *flops_per_s = best;
+  return BMPC_OK;
+}
+
 int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
                      double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err, void* workspace, void* cuda_stream) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch: null handle");
@@ -182,13 +256,6 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
   return BMPC_OK;
 }
 
-static int ensure_dbuf(bmpc_handle* h, size_t bytes) {
-  if (h->dbuf_bytes >= bytes) return BMPC_OK;
-  if (h->dbuf) { cudaFree(h->dbuf); h->dbuf = nullptr; h->dbuf_bytes = 0; }
-  CU(cudaMalloc(&h->dbuf, bytes));
-  h->dbuf_bytes = bytes;
-  return BMPC_OK;
-}
 
 int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
                           double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err) {

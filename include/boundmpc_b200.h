@@ -102,6 +102,11 @@ int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const d
  * number of kernel launches issued by this library since the handle was created */
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
+/* Diagnostics for bench.py's roofline denominator (MEASURED_PEAKS.json has no FP64
+ * entry): runs a register-resident DFMA loop (kind 0) or an mma.sync.m8n8k4.f64 DMMA loop
+ * (kind 1) on every SM of the handle's device and returns the sustained rate in FLOP/s. */
+int bmpc_fp64_peak(bmpc_handle* h, int32_t kind, double* flops_per_s);
+
 const char* bmpc_last_error(void);
 
 #ifdef __cplusplus

@@ -67,7 +67,7 @@ def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
     return dict(x=x, g=g, lam_g=lg, lam_x=lx, f=f, iters=it, status=st, kkt=kkt)
 
 
-def evaluate(x, p, lam=None, N=10, S=4, dt=0.1):
+def evaluate(x, p, lam=None, N=10, S=4, dt=0.1, want_jac=True, want_hess=True):
     x = np.ascontiguousarray(np.atleast_2d(x), float)
     p = np.ascontiguousarray(np.atleast_2d(p), float)
     B, n = x.shape
@@ -75,7 +75,8 @@ def evaluate(x, p, lam=None, N=10, S=4, dt=0.1):
     cfg = make_cfg(N, S, dt)
     lam = None if lam is None else np.ascontiguousarray(np.atleast_2d(lam), float)
     f, g, d, grad = np.empty(B), np.empty((B, m)), np.empty((B, 12 * N)), np.empty((B, n))
-    jac, hess = np.empty((B, 48 * N, n)), np.empty((B, n, n))
+    jac = np.empty((B, 48 * N, n)) if want_jac else None
+    hess = np.empty((B, n, n)) if want_hess else None
     rc = lib().emu_eval(ctypes.byref(cfg), B, _p(x), _p(p), _p(lam), _p(f), _p(g), _p(d), _p(grad), _p(jac), _p(hess))
     assert rc == 0
     return dict(f=f, g=g, d=d, grad=grad, jac=jac, hess=hess)

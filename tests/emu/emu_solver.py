@@ -16,6 +16,9 @@ class EmuSolver:
     def solve_batch(self, x0, p, out=None):
         return emu.solve(x0, p, self.N, self.nr_segs, self.dt, self.tol)
 
+    def eval_batch(self, x, p, lam=None, want_jac=True, want_hess=True):
+        return emu.evaluate(x, p, lam, self.N, self.nr_segs, self.dt, want_jac, want_hess)
+
     def __call__(self, x0=None, p=None, **kw):
         r = self.solve_batch(np.asarray(x0, float).reshape(1, -1), np.asarray(p, float).reshape(1, -1))
         self._stats = dict(iter_count=int(r['iters'][0]), success=int(r['status'][0]) == 0, return_status=str(r['status'][0]))
