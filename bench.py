@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched solves of BoundMPC's per-step OCP.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4], the configuration the metric's target is quoted on): the
+65,536 mixed experiment1 / experiment2 instances, sharded contiguously, 8,192 instances per
+GPU (weak scaling: N GPUs solve 8,192 N instances; N = 8 is the full config).  A "step" is one
+pass over the shard: one launch of the solver kernel on inputs already resident in HBM, plus —
+for N > 1 — the NCCL all-gather of the solutions and statistics.  `value` = instances of all
+ranks / device time (CUDA events on the launching stream, max over ranks).  `e2e` is the same
+step through the host-pointer C-ABI entry (`bmpc_solve_batch_host`: pinned host buffers,
+host-to-device and device-to-host copies inside the timed region).
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads)
+on a bounded sample of the same workload: CasADi / Ipopt / MUMPS cannot be installed offline
+(DESIGN.md "Oracle"), so the reference arm is the oracle port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "batched OCP solves/sec"
+UNIT = "solves/s"
+PER_GPU = 8192
+TOL = 1e-9
+# algorithmic flops of one interior-point iteration of one instance:
+# N (266,517 factorisation + 18,432 solve + 12,000 evaluation)
+F_ITER = {10: 2.97e6, 20: 5.94e6}
+# algorithmic HBM bytes per instance: x0, p in; x, g, lam_g, lam_x, f, kkt, iters, status out
+IO_BYTES = {10: 21504, 20: 38944}
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def load_inputs(solver, rank, world, per_gpu, workers):
+    from boundmpc_b200 import batches
+    t = time.perf_counter()
+    x0, p, scale = batches.make_batch(solver, ("exp1", "exp2"), rank * per_gpu, per_gpu, n=10, bound_scale=True,
+                                      workers=workers, return_scales=True)
+    return x0, p, scale, time.perf_counter() - t
+
+
+def cpu_solves_per_s(x0, p, cores, budget_s, tol=TOL):
+    """Oracle port on `cores` host threads (ctypes releases the GIL), time-boxed: every thread pulls
+    the next instance until the budget is spent.  Returns (solves/s, solved, iteration mean)."""
+    from oracle import oracle as O
+    O.lib()
+    lock = threading.Lock()
+    state = {"next": 0, "done": 0, "iters": 0, "fail": 0}
+    t0 = time.perf_counter()
+
+    def work():
+        while True:
+            with lock:
+                i = state["next"]
+                if i >= len(x0) or time.perf_counter() - t0 > budget_s:
+                    return
+                state["next"] += 1
+            r = O.solve(x0[i], p[i], tol=tol)
+            with lock:
+                state["done"] += 1
+                state["iters"] += r["iters"]
+                state["fail"] += int(r["status"] != 0)
+
+    th = [threading.Thread(target=work) for _ in range(cores)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    el = time.perf_counter() - t0
+    return state["done"] / el, state["done"], state["iters"] / max(1, state["done"]), state["fail"], el
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--per-gpu", type=int, default=PER_GPU)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of wall time for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the solver has no CPU path)")
+    torch.cuda.set_device(local)
+    from boundmpc_b200 import build as bld
+    bld.build()
+    from boundmpc_b200.ocp import default_solver
+    solver = default_solver(N=10, nr_segs=4, dt=0.1, solver_opts={"b200": {"tol": TOL}}, device=local)
+    cores = os.cpu_count() or 1
+    per_gpu = args.per_gpu
+    x0, p, scale, t_gen = load_inputs(solver, rank, world, per_gpu, workers=max(1, min(16, cores // max(1, world))))
+    n, m, npar = solver.n, solver.m, solver.np
+    config = {"workload": f"mixed_65536 shard: {per_gpu} mixed experiment1/experiment2 OCP instances per GPU "
+                          f"(BASELINE configs[4]; N=8 GPUs = the full 65,536)",
+              "instances_per_gpu": per_gpu, "total_instances": per_gpu * max(1, world), "horizon_N": 10, "nr_segs": 4,
+              "n_var": n, "n_con": m, "tol": TOL,
+              "l2": f"inputs+outputs {per_gpu * IO_BYTES[10] / 1e6:.0f} MB per step (> 126 MB L2), no explicit flush",
+              "parallelism": f"independent instances, contiguous shards over {max(1, world)} GPU(s)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU restatement)
+    if args.impl == "reference":
+        sample = min(per_gpu, 4 * cores)
+        for _ in range(args.warmup):
+            cpu_solves_per_s(x0[:cores], p[:cores], cores, 1e9)
+        t0 = time.perf_counter()
+        solved = iters = fails = 0
+        for k in range(args.steps):
+            lo = (k * sample) % max(1, per_gpu - sample + 1)
+            _, d, itm, fl, _ = cpu_solves_per_s(x0[lo:lo + sample], p[lo:lo + sample], cores, 1e9)
+            solved += d; iters += itm * d; fails += fl
+        el = time.perf_counter() - t0
+        v = solved / el
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{sample} instances of the workload per step x {args.steps} steps, oracle/ "
+                                           f"interior-point port at tol {TOL:g} (CasADi/Ipopt not installable offline), "
+                                           f"mean {iters / max(1, solved):.1f} iterations, {fails} failures"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peak_dfma = solver.fp64_peak(0)
+    peak_dmma = solver.fp64_peak(1)
+    xd, pd = torch.from_numpy(x0).to(dev), torch.from_numpy(p).to(dev)
+    out = solver.solve_batch(xd, pd)
+    torch.cuda.synchronize()
+    from boundmpc_b200 import sharding
+    total = per_gpu * world
+    gbuf = sharding.gather_buffers(total, world, n, dev) if world > 1 else None
+    gathered = {}
+
+    ev_k = []
+
+    def step(timed):
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        solver.solve_batch(xd, pd, out)
+        if timed:
+            b.record()
+            ev_k.append((a, b))
+        if world > 1:   # NCCL gather of solutions and statistics
+            gathered.update(sharding.gather_results(out, total, rank, world, gbuf))
+
+    for _ in range(args.warmup):
+        step(False)
+    launches0 = solver.launch_count()
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ck = clocks.stop()
+    launches = solver.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_k]))
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    iters = out["iters"].cpu().numpy()
+    status = out["status"].cpu().numpy()
+    kkt = out["kkt"].cpu().numpy()
+    ok = int((status == 0).sum())
+    cnt = torch.tensor([ok, int(iters.sum()), per_gpu], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+        assert int((gathered["status"] == 0).sum().item()) == int(cnt[0].item())
+
+    # ---- end to end through the host-pointer C-ABI entry, pinned host buffers
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+    hx0, hp = pinned((per_gpu, n)), pinned((per_gpu, npar))
+    hx0[:], hp[:] = x0, p
+    hout = {"x": pinned((per_gpu, n)), "g": pinned((per_gpu, m)), "lam_g": pinned((per_gpu, m)), "lam_x": pinned((per_gpu, n)),
+            "f": pinned((per_gpu,)), "kkt": pinned((per_gpu,)), "iters": pinned((per_gpu,), torch.int32),
+            "status": pinned((per_gpu,), torch.int32)}
+    for _ in range(2):
+        solver.solve_batch(hx0, hp, hout)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.solve_batch(hx0, hp, hout)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_same = bool(np.array_equal(hout["x"], out["x"].cpu().numpy()))
+    h2d = per_gpu * (n + npar) * 8
+    d2h = per_gpu * ((2 * n + 2 * m) * 8 + 8 + 8 + 4 + 4)
+
+    # ---- single-instance latency (B = 1 through the same host entry), p50 over 64 instances
+    lat = []
+    for i in range(min(64, per_gpu)):
+        t = time.perf_counter()
+        solver.solve_batch(x0[i:i + 1], p[i:i + 1])
+        lat.append((time.perf_counter() - t) * 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    sum_iters = float(cnt[1].item())
+    ach = float(iters.sum()) * F_ITER[10] / (k_ms * 1e-3)          # rank 0's kernel: flop / s
+    hbm = per_gpu * IO_BYTES[10] / (k_ms * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    line = {"metric": METRIC, "value": total * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": max(1, world),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "roofline": {"bound": "fp64", "achieved": ach / 1e12, "peak": peak_dfma / 1e12, "unit": "TFLOP/s",
+                         "frac": ach / peak_dfma, "traffic": traffic,
+                         "note": "k_solve, algorithmic flops = sum of interior-point iterations x 2.97 MFLOP (SURVEY 8d) / mean "
+                                 "CUDA-event launch duration; peak = DFMA loop measured in this run (no FP64 entry in "
+                                 f"MEASURED_PEAKS.json); DMMA m8n8k4 loop measured {peak_dmma / 1e12:.1f} TFLOP/s",
+                         "kernel_ms": k_ms,
+                         "hbm": {"achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak,
+                                 "peak_source": "measured" if peaks else "fallback"}},
+            "e2e": {"value": total * args.steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "bitwise_equal_to_device_path": e2e_same},
+            "gpu_launches": launches,
+            "clocks": ck,
+            "solver": {"success": int(cnt[0].item()), "instances": total, "iters_mean": sum_iters / total,
+                       "iters_max_rank0": int(iters.max()), "kkt_max_rank0": float(kkt[status == 0].max()) if ok else None,
+                       "perturbation_scale_hist_rank0": {str(v): int((scale == v).sum()) for v in np.unique(scale)},
+                       "input_generation_s": t_gen},
+            "latency_b1_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "max": float(max(lat)),
+                              "what": "one instance through bmpc_solve_batch_host incl. H2D/D2H, wall clock"}}
+    if world == 1 and not args.no_cpu_baseline:
+        v, d, itm, fl, el = cpu_solves_per_s(x0, p, cores, args.cpu_budget)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"first {d} instances of the workload in {el:.1f} s, oracle/ interior-point port at tol "
+                                          f"{TOL:g} on {cores} threads (CasADi/Ipopt not installable offline), mean {itm:.1f} "
+                                          f"iterations, {fl} failures"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

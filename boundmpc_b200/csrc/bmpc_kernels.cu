@@ -17,6 +17,10 @@ using namespace bmpc;
 #ifndef BMPC_MAX_THREADS
 #define BMPC_MAX_THREADS 256
 #endif
+#ifndef BMPC_DEFAULT_THREADS
+#define BMPC_DEFAULT_THREADS 256
+#define BMPC_DEFAULT_CTAS 1
+#endif
 
 struct BatchIO {
   const double* x0; const double* p;
@@ -24,8 +28,9 @@ struct BatchIO {
   int32_t *iters, *status;
 };
 
-__global__ void __launch_bounds__(BMPC_MAX_THREADS) k_solve(const __grid_constant__ Config C, int batch, BatchIO io, double* ws,
-                                                            size_t ws_stride, unsigned int* counter) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C, int batch, BatchIO io, double* ws,
+                                                         size_t ws_stride, unsigned int* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
@@ -42,6 +47,15 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_solve(const __grid_constan
     solve_instance(cx, C, W, S, ii);
   }
 }
+
+// launch variants: (threads per CTA, resident CTAs per SM the register budget is compiled for)
+typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, unsigned int*);
+struct SolveVariant { int threads, minb; solve_fn fn; };
+static const SolveVariant kVariants[] = {
+    {256, 1, k_solve<256, 1>}, {256, 2, k_solve<256, 2>}, {128, 2, k_solve<128, 2>},
+    {128, 3, k_solve<128, 3>}, {128, 4, k_solve<128, 4>}, {128, 5, k_solve<128, 5>},
+};
+static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 struct EvalBatchIO {
   const double *x, *p, *lam;
@@ -116,7 +130,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 
 struct bmpc_handle {
   Config C;
-  int device, threads, sms, ctas_per_sm;
+  int device, threads, sms, ctas_per_sm, variant;
   size_t ws_stride;    // doubles per CTA slot
   int64_t launches;
   // cached device buffers of the host-pointer entry points
@@ -157,18 +171,23 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
   h->sms = prop.multiProcessorCount;
-  h->threads = cfg->threads > 0 ? cfg->threads : BMPC_MAX_THREADS;
-  if (h->threads > BMPC_MAX_THREADS || h->threads % 32) { delete h; return fail(BMPC_E_INVALID, "bmpc_create: threads must be a multiple of 32 and <= 256"); }
-  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  // launch shape: cfg->threads (or BMPC_THREADS) and BMPC_CTAS_PER_SM select the compiled variant
+  const char* envt = getenv("BMPC_THREADS");
+  const char* envc = getenv("BMPC_CTAS_PER_SM");
+  int want_t = cfg->threads > 0 ? cfg->threads : (envt ? atoi(envt) : BMPC_DEFAULT_THREADS);
+  int want_c = envc ? atoi(envc) : BMPC_DEFAULT_CTAS;
+  h->variant = -1;
+  for (int v = 0; v < kNumVariants; v++)
+    if (kVariants[v].threads == want_t && kVariants[v].minb == want_c) h->variant = v;
+  if (h->variant < 0) { delete h; return fail(BMPC_E_INVALID, "bmpc_create: no kernel variant for this threads / CTAs-per-SM combination"); }
+  h->threads = want_t;
+  e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, h->threads, sizeof(Smem));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kVariants[h->variant].fn, h->threads, sizeof(Smem));
   if (e != cudaSuccess || occ < 1) { delete h; return fail(BMPC_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
-  const char* env = getenv("BMPC_CTAS_PER_SM");
-  h->ctas_per_sm = env ? atoi(env) : occ;
-  if (h->ctas_per_sm < 1) h->ctas_per_sm = 1;
-  if (h->ctas_per_sm > occ) h->ctas_per_sm = occ;
+  h->ctas_per_sm = want_c < occ ? want_c : occ;
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
   h->launches = 0;
   h->dbuf = nullptr; h->dbuf_bytes = 0;
@@ -250,7 +269,7 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
   CU(cudaMemsetAsync(counter, 0, 256, st));
   BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status};
   const int grid = grid_for(h, batch);
-  k_solve<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, counter);
+  kVariants[h->variant].fn<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, counter);
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

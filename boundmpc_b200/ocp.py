@@ -95,6 +95,12 @@ class BatchSolver:
     def launch_count(self):
         return int(self._lib.bmpc_launch_count(self._h))
 
+    def fp64_peak(self, kind=0):
+        """Measured FP64 rate of the device in FLOP/s: kind 0 = DFMA loop, 1 = DMMA (mma.sync m8n8k4) loop."""
+        v = ctypes.c_double()
+        _cabi.check(self._lib.bmpc_fp64_peak(self._h, int(kind), ctypes.byref(v)), "bmpc_fp64_peak")
+        return v.value
+
     # ---- batched entry
     def solve_batch(self, x0, p, out=None):
         """x0 [B, n], p [B, np] -> dict of x, g, lam_g, lam_x [B, .], f, kkt [B], iters, status [B].

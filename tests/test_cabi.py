@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "boundmpc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bmpc_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(bmpc_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_builds_and_exports_header_symbols():
