@@ -30,8 +30,41 @@ namespace bmpc {
 
 struct Ctx {
   int tid, nt;
-  double* red;  // shared scratch for block reductions (>= 40 doubles)
+  double* red;  // shared scratch for block reductions (8 x 32 doubles)
 };
+BMPC_DEV int ctx_warp(const Ctx& cx) { return cx.tid >> 5; }
+BMPC_DEV int ctx_nwarps(const Ctx& cx) { return (cx.nt + 31) >> 5; }
+
+// One 8 x 8 output tile of a matrix product on the FP64 tensor-core path, executed by one warp:
+//   C(r, c) = sum_{kk < 4 ksteps} a(r, kk) * b(kk, c),   r, c in 0..7,
+// with `mma.sync.aligned.m8n8k4.f64` (SASS DMMA).  `a` and `b` are element accessors into shared
+// memory; `epi(r, c, value)` receives every element of the tile exactly once (two per lane).
+// Fragment layout (PTX ISA, m8n8k4 .f64): lane l holds A(l / 4, l % 4), B(l % 4, l / 4) and
+// C(l / 4, 2 (l % 4) + {0, 1}).  The host-emulation build evaluates the same tile with loops.
+template <class FA, class FB, class FE>
+BMPC_DEV void mma_tile(const Ctx& cx, int ksteps, FA a, FB b, FE epi) {
+#ifdef BMPC_HOST_EMU
+  (void)cx;
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 8; c++) {
+      double v = 0.0;
+      for (int kk = 0; kk < 4 * ksteps; kk++) v += a(r, kk) * b(kk, c);
+      epi(r, c, v);
+    }
+#else
+  const int lane = cx.tid & 31, r = lane >> 2, q = lane & 3;
+  double c0 = 0.0, c1 = 0.0;
+  for (int ks = 0; ks < ksteps; ks++) {
+    const double av = a(r, 4 * ks + q), bv = b(4 * ks + q, r);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+  }
+  epi(r, 2 * q, c0);
+  epi(r, 2 * q + 1, c1);
+#endif
+}
+// tiles of a phase are dealt to the warps of the CTA round-robin
+#define TILE_FOR(t, n) for (int t = ctx_warp(cx); t < (n); t += ctx_nwarps(cx))
 
 // ---- stage layout (casadi_ocp_formulation.py:90-153) ----------------------
 constexpr int NX = 44;   // variables per stage: [u(7) u_phi q(7) dq(7) ddq(7) p_pos(3) p_rot(3) v_lin(3) v_ang(3) phi dphi ddphi]

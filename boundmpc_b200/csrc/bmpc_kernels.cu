@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  build_tables(cx, C, S);
   for (;;) {
     if (threadIdx.x == 0) S.flag[2] = (int)atomicAdd(counter, 1u);
     __syncthreads();
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  build_tables(cx, C, S);
   const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
     EvalIO e{io.x + b * n, io.p + (size_t)b * C.np, io.lam ? io.lam + b * nl : nullptr, io.f ? io.f + b : nullptr,

@@ -18,25 +18,42 @@
 
 namespace bmpc {
 
-// shared-memory working set of one CTA (doubles)
+// shared-memory working set of one CTA (doubles).  Leading dimensions 44 / 52 / 12 are = 4 or 12
+// (mod 16), which makes the DMMA fragment loads (8 rows x 4 columns of doubles per half-warp)
+// bank-conflict free; arrays read as tile operands carry the few pad elements a partial edge
+// tile touches (their products only reach tile elements that are never stored).
+constexpr int LDM = NX;        // 44
+constexpr int LDY = NZ;        // 52
+constexpr int LDQ = 12;
 struct Smem {
-  double M[NX * NX];     // W~_kk + P_{k+1}, then reused for P_k
-  double GK[NK * NZ];    // kinematic rows of G_k
-  double Y[NE * NZ];     // M_xx G
-  double Z[NU * NZ];     // M_ux G
-  double Q[NZ * NZ];     // upper triangle of E^T M E + O-terms
-  double OU[NU * NX];    // rows u_k of the off-diagonal Hessian block W~_{k,k-1}
-  double pv[NX];         // p_{k+1} / p_k
-  double mv[NX];         // g^_k + p_{k+1}
-  double tv[NE];         // M_xx c + m_x
-  double tu[NU];
+  double M[48 * LDM];          // W~_kk + P_{k+1}, overwritten by P_k
+  double GK[NK * NZ + 4];      // kinematic rows of G_k = [A_hat | B]
+  double YZ[NX * LDY];         // M[:, x] G  (rows 0..7 = u rows "Z", rows 8..43 = x rows "Y")
+  double Qu[56 * LDQ];         // columns u_k of Q: rows 0..43 = Q_su, rows 44..51 = Q_uu
+  double Ks[NU * NX + 4];      // feedback gain K_k
+  double pv[NX];               // p_{k+1} / p_k
+  double mv[NX];               // g^_k + p_{k+1}
+  double tv[NX];               // M[:, x] c + m   (rows 0..7 = u part)
   double qv[NZ];
-  double Lc[NU * NU];    // Cholesky factor of Q_uu
+  double cv[NE];               // c_k
+  double kapv[NU];
   double odv[6];
-  double red[8 * 32];    // block reductions
-  double filt[2 * 64];   // filter entries (theta, phi)
+  double tcc[NZ * 3];          // constant rows of G per column: coefficients ...
+  int tcr[NZ * 3];             // ... and x-row indices (triv_col as a table)
+  double red[8 * 32];          // block reductions
+  double filt[2 * 64];         // filter entries (theta, phi)
   int flag[4];
 };
+
+// table form of triv_col, built once per kernel
+BMPC_DEV void build_tables(const Ctx& cx, const Config& C, Smem& S) {
+  PAR_FOR(col, NZ) {
+    int rr[3]; double cf[3];
+    const int nt = triv_col(C, col, rr, cf);
+    for (int t = 0; t < 3; t++) { S.tcr[3 * col + t] = t < nt ? rr[t] : 0; S.tcc[3 * col + t] = t < nt ? cf[t] : 0.0; }
+  }
+  BMPC_SYNC();
+}
 
 struct KktCoef {         // constants of the velocity / acceleration tracking Hessian
   double w2, w5, w7, w8, w9, w10, w11, w12, w13, idt;
@@ -164,161 +181,183 @@ BMPC_DEV void kkt_build(const Ctx& cx, const Config& C, const Work& W, const Kkt
   BMPC_SYNC();
 }
 
+// 8 x 8 Cholesky factor of Q_uu in registers; Lr holds L with the RECIPROCAL diagonal.  Every thread
+// that needs the factor computes it itself from shared memory (no broadcast, no extra barrier; the
+// result is identical in all threads, so the inertia verdict is CTA-uniform).
+BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
+#pragma unroll
+  for (int i = 0; i < NU; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) A[i][j] = Qu[(NX + j) * LDQ + i];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < NU; j++) {
+    double d = A[j][j];
+#pragma unroll
+    for (int l = 0; l < j; l++) d -= A[j][l] * A[j][l];
+    if (!(d > 1e-14)) ok = false;
+    const double inv = 1.0 / sqrt(d > 1e-14 ? d : 1.0);
+    A[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < NU; i++) {
+      double e = A[i][j];
+#pragma unroll
+      for (int l = 0; l < j; l++) e -= A[i][l] * A[j][l];
+      A[i][j] = e * inv;
+    }
+  }
+  return ok;
+}
+
 // One backward Riccati step for stage k.  On entry S.M = P_{k+1} (zero for k = N-1), S.pv = p_{k+1}.
 // On exit S.M = P_k, S.pv = p_k, gains stored in W.Kk / W.kap.  Returns false if Q_uu is not PD.
+// The dense block products run as 8 x 8 DMMA tiles (mma_tile); the constant rows of G are applied
+// from the tcr / tcc tables in the tile epilogues.
 BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
-  const double* c = W.c + NE * k;
   const double* Wd = W.Wd + (size_t)k * NX * NX;
+  const double* OUa = W.OUa + (size_t)k * NU * NX;
+  const bool first = k == 0;      // stage 0: the previous block is fixed -> only the u-columns
   PAR_FOR(i, NX * NX) S.M[i] += Wd[i] + ((i % (NX + 1)) == 0 ? delta_w : 0.0);
   PAR_FOR(i, NK * NZ) S.GK[i] = rec[R_GK + i];
   PAR_FOR(i, NX) S.mv[i] = W.gh[NX * k + i] + S.pv[i];
-  if (k > 0) {
-    const double* OUa = W.OUa + (size_t)k * NU * NX;
-    PAR_FOR(i, NU * NX) S.OU[i] = OUa[i];
-    PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * rec[R_DPD + m] * kc.idt;
-  }
+  PAR_FOR(i, NE) S.cv[i] = W.c[NE * k + i];
+  PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * rec[R_DPD + m] * kc.idt;
   BMPC_SYNC();
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
-  const int ncol = k > 0 ? NZ : NU;          // stage 0: the previous block is fixed -> only the u-columns
-  const int c0 = k > 0 ? 0 : NX;
-  // Y = M_xx G, Z = M_ux G, t = M_xx c + m_x, tu = M_ux c + m_u
-  PAR_FOR(it, (NE + NU) * ncol) {
-    const int row = it / ncol, col = c0 + it - ncol * row;
-    const double* Mr = row < NE ? S.M + (8 + row) * NX + 8 : S.M + (row - NE) * NX + 8;
-    double a = 0.0;
+  // ---- YZ = M[:, x] G  (44 x 52): 6 x 7 tiles, inner dimension = the 12 kinematic rows
+  {
+    const int tj0 = first ? 5 : 0, ntj = 7 - tj0;
+    TILE_FOR(t, 6 * ntj) {
+      const int ti = t / ntj, tj = tj0 + t - ntj * ti;
+      mma_tile(cx, 3,
+               [&](int r, int kk) { return S.M[(8 * ti + r) * LDM + 8 + rKIN + kk]; },
+               [&](int kk, int c) { return S.GK[kk * NZ + 8 * tj + c]; },
+               [&](int r, int c, double v) {
+                 const int i = 8 * ti + r, col = 8 * tj + c;
+                 if (i < NX && col < NZ) {
+                   const double* Mr = S.M + i * LDM + 8;
 #pragma unroll
-    for (int r = 0; r < NK; r++) a += Mr[rKIN + r] * S.GK[r * NZ + col];
-    int rr[3]; double cf[3];
-    const int nt = triv_col(C, col, rr, cf);
-    for (int t = 0; t < nt; t++) a += cf[t] * Mr[rr[t]];
-    if (row < NE) S.Y[row * NZ + col] = a; else S.Z[(row - NE) * NZ + col] = a;
-  }
-  PAR_FOR(row, NE + NU) {
-    const double* Mr = row < NE ? S.M + (8 + row) * NX + 8 : S.M + (row - NE) * NX + 8;
-    double a = row < NE ? S.mv[8 + row] : S.mv[row - NE];
-    for (int l = 0; l < NE; l++) a += Mr[l] * c[l];
-    if (row < NE) S.tv[row] = a; else S.tu[row - NE] = a;
+                   for (int q = 0; q < 3; q++) v += S.tcc[3 * col + q] * Mr[S.tcr[3 * col + q]];
+                   S.YZ[i * LDY + col] = v;
+                 }
+               });
+    }
+    // t = M[:, x] c + m
+    PAR_FOR(i, NX) {
+      const double* Mr = S.M + i * LDM + 8;
+      double a0 = S.mv[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int l = 0; l < NE; l += 4) { a0 += Mr[l] * S.cv[l]; a1 += Mr[l + 1] * S.cv[l + 1]; a2 += Mr[l + 2] * S.cv[l + 2]; a3 += Mr[l + 3] * S.cv[l + 3]; }
+      S.tv[i] = (a0 + a1) + (a2 + a3);
+    }
   }
   BMPC_SYNC();
-  // Q = G^T Y + U^T Z + Z^T U + U^T M_uu U + (E^T O [I 0] + transpose),  upper triangle a <= b
-  PAR_FOR(it, ncol * ncol) {
-    const int ai = it / ncol, bi = it - ncol * ai;
-    if (ai > bi) continue;
-    const int a = c0 + ai, b = c0 + bi;
-    double v = 0.0;
+  // ---- columns u_k of Q = E^T M E + O-terms  (52 x 8): 7 tiles
+  {
+    const int ti0 = first ? 5 : 0;
+    TILE_FOR(t, 7 - ti0) {
+      const int ti = ti0 + t;
+      mma_tile(cx, 3,
+               [&](int r, int kk) { return S.GK[kk * NZ + 8 * ti + r]; },
+               [&](int kk, int c) { return S.YZ[(8 + rKIN + kk) * LDY + NX + c]; },
+               [&](int r, int j, double v) {
+                 const int a = 8 * ti + r;
+                 if (a >= NZ || (first && a < NX)) return;
 #pragma unroll
-    for (int r = 0; r < NK; r++) v += S.GK[r * NZ + a] * S.Y[(rKIN + r) * NZ + b];
-    int rr[3]; double cf[3];
-    const int nt = triv_col(C, a, rr, cf);
-    for (int t = 0; t < nt; t++) v += cf[t] * S.Y[rr[t] * NZ + b];
-    if (a >= NX) v += S.Z[(a - NX) * NZ + b];
-    if (b >= NX) v += S.Z[(b - NX) * NZ + a];
-    if (a >= NX && b >= NX) v += S.M[(a - NX) * NX + (b - NX)];
-    if (k > 0) {
-      // EO = E^T O (52 x 44): contributes EO[a][b] for b < 44 and EO[b][a] for a < 44.
-      // O_x: rows v_{k+1} (x-rows 27..32) x cols v_k (35..40): ovv on the diagonal; row ddphi (x-row 35): odv
-      if (b < NX && b >= oVLIN && b < oVLIN + 6) {
-        const int m = b - oVLIN;
-        const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : (a == NX + oUPHI ? C.c_u : 0.0));
-        v += S.GK[(6 + m) * NZ + a] * ovv + g35 * S.odv[m];
-      }
-      if (a < NX) {
-        if (b >= NX) v += S.OU[(b - NX) * NX + a];
-        if (a >= oVLIN && a < oVLIN + 6) {
-          const int m = a - oVLIN;
-          const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : (b == NX + oUPHI ? C.c_u : 0.0));
-          v += S.GK[(6 + m) * NZ + b] * ovv + g35 * S.odv[m];
+                 for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + NX + j];
+                 if (a < NX) {
+                   v += S.YZ[j * LDY + a] + OUa[j * NX + a];
+                   if (a >= oVLIN && a < oVLIN + 6) v += S.GK[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
+                 } else {
+                   const int i = a - NX;
+                   v += S.YZ[i * LDY + NX + j] + S.YZ[j * LDY + NX + i] + S.M[i * LDM + j];
+                 }
+                 S.Qu[a * LDQ + j] = v;
+               });
+    }
+    // q = G^T t + U^T t_u + [O_x^T c ; 0]
+    PAR_FOR(ai, first ? NU : NZ) {
+      const int a = first ? NX + ai : ai;
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < NK; r++) v += S.GK[r * NZ + a] * S.tv[8 + rKIN + r];
+#pragma unroll
+      for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.tv[8 + S.tcr[3 * a + q]];
+      if (a >= NX) v += S.tv[a - NX];
+      if (!first && a >= oVLIN && a < oVLIN + 6) v += ovv * S.cv[27 + (a - oVLIN)] + S.odv[a - oVLIN] * S.cv[35];
+      S.qv[a] = v;
+    }
+  }
+  BMPC_SYNC();
+  // ---- gains: K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u; the factor is recomputed per thread
+  double* K = W.Kk + (size_t)k * NU * NX;
+  double* kap = W.kap + k * NU;
+  bool ok;
+  {
+    double L[NU][NU];
+    ok = chol8(S.Qu, L);
+    if (ok) {
+      PAR_FOR(col, (first ? 0 : NX) + 1) {
+        const bool isk = col == (first ? 0 : NX);
+        double bcol[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) bcol[i] = isk ? -S.qv[NX + i] : -S.Qu[col * LDQ + i];
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+          double a = bcol[i];
+#pragma unroll
+          for (int l = 0; l < i; l++) a -= L[i][l] * bcol[l];
+          bcol[i] = a * L[i][i];
+        }
+#pragma unroll
+        for (int i = NU - 1; i >= 0; i--) {
+          double a = bcol[i];
+#pragma unroll
+          for (int l = i + 1; l < NU; l++) a -= L[l][i] * bcol[l];
+          bcol[i] = a * L[i][i];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+          if (isk) { kap[i] = bcol[i]; S.kapv[i] = bcol[i]; }
+          else { K[i * NX + col] = bcol[i]; S.Ks[i * NX + col] = bcol[i]; }
         }
       }
     }
-    S.Q[a * NZ + b] = v;
   }
-  // q = G^T t + U^T tu + [O_x^T c ; 0]
-  PAR_FOR(ai, ncol) {
-    const int a = c0 + ai;
-    double v = GT_vec(C, S.GK, S.tv, a);
-    if (a >= NX) v += S.tu[a - NX];
-    if (k > 0 && a >= oVLIN && a < oVLIN + 6) v += ovv * c[27 + (a - oVLIN)] + S.odv[a - oVLIN] * c[35];
-    S.qv[a] = v;
-  }
+  if (!ok) return false;
   BMPC_SYNC();
-  // Cholesky of Q_uu (8 x 8) in registers by one thread; Lc holds L with the RECIPROCAL diagonal
-  if (cx.tid == 0) {
-    double A[NU][NU];
+  if (first) return true;
+  // ---- P_k = Q_ss + Q_su K  (symmetric; upper tiles, mirrored), p_k = q_s + Q_su kappa
+  TILE_FOR(t, 21) {
+    int ti = 0, rem = t;
+    while (rem >= 6 - ti) { rem -= 6 - ti; ti++; }
+    const int tj = ti + rem;
+    mma_tile(cx, 5,
+             [&](int r, int kk) { return kk < NK ? S.GK[kk * NZ + 8 * ti + r] : S.Qu[(8 * ti + r) * LDQ + kk - NK]; },
+             [&](int kk, int c) { return kk < NK ? S.YZ[(8 + rKIN + kk) * LDY + 8 * tj + c] : S.Ks[(kk - NK) * NX + 8 * tj + c]; },
+             [&](int r, int c, double v) {
+               const int a = 8 * ti + r, b = 8 * tj + c;
+               if (a >= NX || b >= NX || a > b) return;
 #pragma unroll
-    for (int i = 0; i < NU; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) A[i][j] = S.Q[(NX + j) * NZ + NX + i];
-    int ok = 1;
-#pragma unroll
-    for (int j = 0; j < NU; j++) {
-      double d = A[j][j];
-#pragma unroll
-      for (int l = 0; l < j; l++) d -= A[j][l] * A[j][l];
-      if (!(d > 1e-14)) ok = 0;
-      const double inv = 1.0 / sqrt(d > 1e-14 ? d : 1.0);
-      A[j][j] = inv;
-#pragma unroll
-      for (int i = j + 1; i < NU; i++) {
-        double e = A[i][j];
-#pragma unroll
-        for (int l = 0; l < j; l++) e -= A[i][l] * A[j][l];
-        A[i][j] = e * inv;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NU; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) S.Lc[i * NU + j] = A[i][j];
-    S.flag[0] = ok;
-  }
-  BMPC_SYNC();
-  if (!S.flag[0]) return false;
-  // gains: K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u
-  double* K = W.Kk + (size_t)k * NU * NX;
-  double* kap = W.kap + k * NU;
-  PAR_FOR(col, (k > 0 ? NX : 0) + 1) {
-    const bool isk = col == (k > 0 ? NX : 0);
-    double L[NU][NU], bcol[NU];
-#pragma unroll
-    for (int i = 0; i < NU; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) L[i][j] = S.Lc[i * NU + j];
-#pragma unroll
-    for (int i = 0; i < NU; i++) bcol[i] = isk ? -S.qv[NX + i] : -S.Q[col * NZ + NX + i];
-#pragma unroll
-    for (int i = 0; i < NU; i++) {
-      double a = bcol[i];
-#pragma unroll
-      for (int l = 0; l < i; l++) a -= L[i][l] * bcol[l];
-      bcol[i] = a * L[i][i];
-    }
-#pragma unroll
-    for (int i = NU - 1; i >= 0; i--) {
-      double a = bcol[i];
-#pragma unroll
-      for (int l = i + 1; l < NU; l++) a -= L[l][i] * bcol[l];
-      bcol[i] = a * L[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < NU; i++) { if (isk) kap[i] = bcol[i]; else K[i * NX + col] = bcol[i]; }
-  }
-  BMPC_SYNC();
-  if (k == 0) return true;
-  // P_k = Q_ss + Q_us^T K (symmetric), p_k = q_s + Q_us^T kappa
-  PAR_FOR(it, NX * NX) {
-    const int a = it / NX, b = it - NX * a;
-    if (a > b) continue;
-    double v = S.Q[a * NZ + b];
-#pragma unroll
-    for (int i = 0; i < NU; i++) v += S.Q[a * NZ + NX + i] * K[i * NX + b];
-    S.M[a * NX + b] = v;
-    S.M[b * NX + a] = v;
+               for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + b];
+               // E^T O [I 0] + transpose: rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv
+               if (b >= oVLIN && b < oVLIN + 6) {
+                 const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : 0.0);
+                 v += S.GK[(6 + b - oVLIN) * NZ + a] * ovv + g35 * S.odv[b - oVLIN];
+               }
+               if (a >= oVLIN && a < oVLIN + 6) {
+                 const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : 0.0);
+                 v += S.GK[(6 + a - oVLIN) * NZ + b] * ovv + g35 * S.odv[a - oVLIN];
+               }
+               S.M[a * LDM + b] = v;
+               S.M[b * LDM + a] = v;
+             });
   }
   PAR_FOR(a, NX) {
     double v = S.qv[a];
-    for (int i = 0; i < NU; i++) v += S.Q[a * NZ + NX + i] * kap[i];
+#pragma unroll
+    for (int i = 0; i < NU; i++) v += S.Qu[a * LDQ + i] * S.kapv[i];
     S.pv[a] = v;
   }
   BMPC_SYNC();
