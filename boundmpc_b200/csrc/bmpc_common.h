@@ -25,6 +25,14 @@
 #endif
 
 #define PAR_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nt)
+// items of a phase executed by a single warp (no CTA barrier needed between such phases)
+#ifdef BMPC_HOST_EMU
+#define LANE_FOR(l, n) for (int l = 0; l < (n); l++)
+#define BMPC_WSYNC() ((void)0)
+#else
+#define LANE_FOR(l, n) for (int l = (cx.tid & 31); l < (n); l += 32)
+#define BMPC_WSYNC() __syncwarp()
+#endif
 
 namespace bmpc {
 

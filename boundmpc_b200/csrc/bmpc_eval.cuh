@@ -49,16 +49,20 @@ BMPC_DEV void eval_instance(const Ctx& cx, const Config& C, const Work& W, Smem&
     const KktCoef kc = kkt_coef(C, io.p);
     PAR_FOR(i, n * n) io.hess[i] = 0.0;
     BMPC_SYNC();
-    kkt_build(cx, C, W, kc, 0.0, false);
+    double al[5], be[5]; int off[5];
+    type_coef(C, al, be, off);
     const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
     for (int k = 0; k < N; k++) {
-      PAR_FOR(i, NX * NX) { const int a = i / NX, b = i - NX * a; io.hess[(size_t)(NX * k + a) * n + NX * k + b] = W.Wd[(size_t)k * NX * NX + i]; }
+      const double* rec = W.rec + (size_t)k * R_SIZE;
+      PAR_FOR(i, NX * NX) {
+        const int a = i / NX, b = i - NX * a;
+        io.hess[(size_t)(NX * k + a) * n + NX * k + b] = wd_entry(C, W, kc, al, be, k, a, b);
+      }
       if (k > 0) {
-        const double* rec = W.rec + (size_t)k * R_SIZE;
         PAR_FOR(i, NX * NX) {
           const int a = i / NX, b = i - NX * a;   // row in w_k, col in w_{k-1}
           double v = 0.0;
-          if (a < 8) v = W.OUa[(size_t)k * NU * NX + a * NX + b];
+          if (a < 8) v = ou_entry(rec, al, be, a, b);
           else if (a >= oVLIN && a < oVLIN + 6 && b == a) v = ovv;
           else if (a == oDDPHI && b >= oVLIN && b < oVLIN + 6) v = 2 * kc.w5 * rec[R_DPD + b - oVLIN] * kc.idt;
           io.hess[(size_t)(NX * k + a) * n + NX * (k - 1) + b] = v;

@@ -81,9 +81,9 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       const int k = i / NX, a = i - NX * k;
       double r = W.gradf[i] - W.zL[i] + W.zU[i];
       const double* GKk = W.rec + (size_t)k * R_SIZE + R_GK;
-      if (a < 8) r += GT_vec(C, GKk, W.y + NE * k, NX + a);
+      if (a < 8) r += GT_tab(S, GKk, W.y + NE * k, NX + a);
       else r -= W.y[NE * k + a - 8];
-      if (k + 1 < N) r += GT_vec(C, GKk + R_SIZE, W.y + NE * (k + 1), a);
+      if (k + 1 < N) r += GT_tab(S, GKk + R_SIZE, W.y + NE * (k + 1), a);
       const int ya = (a >= oPPOS && a < oPPOS + 6) ? a - oPPOS : (a == oPHI ? 6 : (a == oDPHI ? 7 : -1));
       if (ya >= 0) {
         const double* JD = W.rec + (size_t)k * R_SIZE + R_JD;
@@ -126,7 +126,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
     if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * fmax(1.0, th_cur); theta_min = 1e-4 * fmax(1.0, th_cur); }
     // ---- search direction with inertia correction
     double dwreg = 0.0;
-    kkt_build(cx, C, W, kkt_coef(C, p), mu, true);
+    kkt_prepare(cx, C, W, mu);
     bool ok = kkt_solve(cx, C, W, p, S, 0.0);
     if (!ok) {
       dwreg = delta_w_last == 0.0 ? 1e-4 : fmax(1e-20, delta_w_last / 3);

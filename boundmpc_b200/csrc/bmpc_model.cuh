@@ -42,14 +42,13 @@ struct Work {
   double *Kk;                                               // [N][8*44]
   double *kap;                                              // [N][8]
   double *cost;                                             // [N]
-  double *Wd;                                               // [N][44*44] diagonal blocks of W~ (without delta_w)
-  double *OUa;                                              // [N][8*44]  rows u_k of the off-diagonal blocks W~_{k,k-1}
+  double *sig;                                              // [n] bound part of the barrier Hessian: z_L / (x - l) + z_U / (u - x)
   double *wp0;                                              // [44] stage-0 "previous block" built from p
 };
 
 BMPC_HD size_t work_doubles(int N) {
   size_t n = (size_t)NX * N, ne = (size_t)NE * N, nd = (size_t)ND * N;
-  return 9 * n + 4 * ne + 7 * nd + (size_t)N * R_SIZE + (size_t)2 * N * F_SIZE + (size_t)N * 8 * NX + (size_t)N * 8 + N + NX + (size_t)N * (NX * NX + NU * NX);
+  return 9 * n + 4 * ne + 7 * nd + (size_t)N * R_SIZE + (size_t)2 * N * F_SIZE + (size_t)N * 8 * NX + (size_t)N * 8 + N + NX + n;
 }
 BMPC_DEV void work_carve(Work& W, double* base, int N) {
   size_t n = (size_t)NX * N, ne = (size_t)NE * N, nd = (size_t)ND * N;
@@ -64,8 +63,7 @@ BMPC_DEV void work_carve(Work& W, double* base, int N) {
   W.Kk = q; q += (size_t)N * 8 * NX;
   W.kap = q; q += (size_t)N * 8;
   W.cost = q; q += N;
-  W.Wd = q; q += (size_t)N * NX * NX;
-  W.OUa = q; q += (size_t)N * NU * NX;
+  W.sig = q; q += n;
   W.wp0 = q; q += NX;
 }
 

@@ -40,6 +40,7 @@ struct Smem {
   double odv[6];
   double tcc[NZ * 3];          // constant rows of G per column: coefficients ...
   int tcr[NZ * 3];             // ... and x-row indices (triv_col as a table)
+  double alc[5], bec[5];       // d q_n / d(um, q, dq, ddq, u) and d dq_n / d(...) of the integrator (type_coef)
   double red[8 * 32];          // block reductions
   double filt[2 * 64];         // filter entries (theta, phi)
   int flag[4];
@@ -52,7 +53,21 @@ BMPC_DEV void build_tables(const Ctx& cx, const Config& C, Smem& S) {
     const int nt = triv_col(C, col, rr, cf);
     for (int t = 0; t < 3; t++) { S.tcr[3 * col + t] = t < nt ? rr[t] : 0; S.tcc[3 * col + t] = t < nt ? cf[t] : 0.0; }
   }
+  if (cx.tid == 0) {
+    S.alc[0] = C.a_um; S.alc[1] = 1.0; S.alc[2] = C.a_dq; S.alc[3] = C.a_ddq; S.alc[4] = C.a_u;
+    S.bec[0] = C.b_um; S.bec[1] = 0.0; S.bec[2] = 1.0; S.bec[3] = C.b_ddq; S.bec[4] = C.b_u;
+  }
   BMPC_SYNC();
+}
+
+// (G_k^T v)[col] with the constant rows taken from the tables
+BMPC_DEV double GT_tab(const Smem& S, const double* GK, const double* v, int col) {
+  double a = 0.0;
+#pragma unroll
+  for (int r = 0; r < NK; r++) a += GK[r * NZ + col] * v[rKIN + r];
+#pragma unroll
+  for (int t = 0; t < 3; t++) a += S.tcc[3 * col + t] * v[S.tcr[3 * col + t]];
+  return a;
 }
 
 struct KktCoef {         // constants of the velocity / acceleration tracking Hessian
@@ -80,40 +95,41 @@ BMPC_DEV int jtype(int a) { return a < 7 ? 0 : (a < 8 ? -1 : (a < 15 ? 1 : (a < 
 BMPC_DEV int jidx(int a) { return a < 7 ? a : (a < 15 ? a - 8 : (a < 22 ? a - 15 : a - 22)); }
 BMPC_DEV int yidx(int a) { return (a >= oPPOS && a < oPPOS + 6) ? a - oPPOS : (a == oPHI ? 6 : (a == oDPHI ? 7 : -1)); }
 
-// One entry (a, b) of the diagonal block W~_kk (gather form: every entry is written by exactly one
-// thread).  barrier = true adds the bound terms and uses the y-block with the slack terms.
-BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, const double* al, const double* be, int k, int a, int b,
-                         bool barrier) {
+// first index of the joint-variable types um, q, dq, ddq inside a stage block, and the stage
+// index of the y-block entries (p_pos, p_rot, phi, dphi)
+BMPC_DEV int joff(int t) { return t == 0 ? oU : (t == 1 ? oQ : (t == 2 ? oDQ : oDDQ)); }
+BMPC_DEV int yrow(int y) { return y < 6 ? oPPOS + y : (y == 6 ? oPHI : oDPHI); }
+
+// constant part of the diagonal of W~_kk (quadratic cost terms, bound_mpc_functions.py:205-246)
+BMPC_DEV double wdiag_const(const KktCoef& kc, const double* rec, int a, bool has_next) {
+  if (a < 7) return 2 * kc.w13;
+  if (a == 7) return 2 * kc.w9;
+  if (a < 15) return 2 * kc.w10;
+  if (a < 22) return 2 * kc.w11;
+  if (a < 29) return 2 * kc.w12;
+  if (a >= oVLIN && a < oVLIN + 6) return 2 * kc.w2 + 2 * kc.w5 * kc.idt * kc.idt * (has_next ? 2.0 : 1.0);
+  if (a == oDDPHI) {
+    double nd = 0.0;
+    for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+    return 2 * kc.w5 * nd + 2 * kc.w8;
+  }
+  return 0.0;
+}
+
+// One entry (a, b) of the diagonal block of the Lagrangian Hessian (dense export for the parity
+// tests only; the solver never forms these blocks, see add_W / adjoint_rhs).
+BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, const double* al, const double* be, int k, int a, int b) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
   const bool has_next = k + 1 < C.N;
-  double v = 0.0;
-  if (a == b) {
-    if (a < 7) v = 2 * kc.w13; else if (a == 7) v = 2 * kc.w9; else if (a < 15) v = 2 * kc.w10;
-    else if (a < 22) v = 2 * kc.w11; else if (a < 29) v = 2 * kc.w12;
-    else if (a >= oVLIN && a < oVLIN + 6) v = 2 * kc.w2 + 2 * kc.w5 * kc.idt * kc.idt * (has_next ? 2.0 : 1.0);
-    else if (a == oDDPHI) {
-      double nd = 0.0;
-      for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
-      v = 2 * kc.w5 * nd + 2 * kc.w8;
-    }
-    if (barrier) {
-      const int gi = NX * k + a;
-      const double lb = C.lb[a], ub = C.ub[a];
-      if (lb > -1e300) v += W.zL[gi] / (W.x[gi] - lb);
-      if (ub < 1e300) v += W.zU[gi] / (ub - W.x[gi]);
-    }
-  }
+  double v = a == b ? wdiag_const(kc, rec, a, has_next) : 0.0;
   const int ya = yidx(a), yb = yidx(b);
   if (ya >= 0 && yb >= 0) {
-    if (barrier) v += rec[R_HYB + ya * 8 + yb];
-    else {
-      if (ya < 7 && yb < 7) v += rec[R_HY + ya * 7 + yb];
-      if (ya == 6 && yb == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * rec[R_HD + r];
-      if (ya == 7 && yb == 7) {
-        double nd = 0.0;
-        for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
-        v += 2 * kc.w2 * nd + 2 * kc.w7;
-      }
+    if (ya < 7 && yb < 7) v += rec[R_HY + ya * 7 + yb];
+    if (ya == 6 && yb == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * rec[R_HD + r];
+    if (ya == 7 && yb == 7) {
+      double nd = 0.0;
+      for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+      v += 2 * kc.w2 * nd + 2 * kc.w7;
     }
   }
   // velocity / acceleration tracking cross terms
@@ -144,41 +160,73 @@ BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, cons
   return v;
 }
 
-// entry (i, col) of the rows u_k of W~_{k,k-1} (kinematic coupling of u_k with (um, q, dq, ddq) of the previous block)
-BMPC_DEV double ou_entry(const Work& W, const double* al, const double* be, int k, int i, int col) {
+// entry (i, col) of the rows u_k of W~_{k,k-1} (kinematic coupling of u_k with (um, q, dq, ddq) of the
+// previous block); al / be may point to the shared tables
+BMPC_DEV double ou_entry(const double* rec, const double* al, const double* be, int i, int col) {
   const int t = jtype(col);
   if (i >= 7 || t < 0) return 0.0;
-  const double* rec = W.rec + (size_t)k * R_SIZE;
   const int j = jidx(col);
   return al[4] * al[t] * rec[R_HQQN + i * 7 + j] + al[4] * be[t] * rec[R_HQDN + i * 7 + j] + be[4] * al[t] * rec[R_HQDN + j * 7 + i];
 }
 
-// All stages at once: W.Wd, W.OUa and g^ (gradient of the barrier problem without the equality multipliers)
-BMPC_DEV void kkt_build(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, double mu, bool barrier) {
-  double al[5], be[5]; int off[5];
-  type_coef(C, al, be, off);
-  const int N = C.N;
-  PAR_FOR(it, N * NX * NX) {
-    const int k = it / (NX * NX), ab = it - k * NX * NX, a = ab / NX, b = ab - NX * a;
-    W.Wd[it] = wd_entry(C, W, kc, al, be, k, a, b, barrier);
-  }
-  PAR_FOR(it, N * NU * NX) {
-    const int k = it / (NU * NX), ic = it - k * NU * NX, i = ic / NX, col = ic - NX * i;
-    W.OUa[it] = k > 0 ? ou_entry(W, al, be, k, i, col) : 0.0;
-  }
-  if (barrier) {
-    PAR_FOR(gi, C.n) {
-      const int k = gi / NX, a = gi - NX * k;
-      double gb = W.gradf[gi];
-      const double lb = C.lb[a], ub = C.ub[a];
-      if (lb > -1e300) gb -= mu / (W.x[gi] - lb);
-      if (ub < 1e300) gb += mu / (ub - W.x[gi]);
-      const int ya = yidx(a);
-      if (ya >= 0) { const double* rec = W.rec + (size_t)k * R_SIZE; gb += mu * rec[R_GJ1 + ya] + rec[R_GJ2 + ya]; }
-      W.gh[gi] = gb;
-    }
+// Once per interior-point iteration: bound part of the barrier Hessian (W.sig) and the gradient g^ of
+// the barrier problem without the equality multipliers (W.gh).
+BMPC_DEV void kkt_prepare(const Ctx& cx, const Config& C, const Work& W, double mu) {
+  PAR_FOR(gi, C.n) {
+    const int k = gi / NX, a = gi - NX * k;
+    double gb = W.gradf[gi], sg = 0.0;
+    const double lb = C.lb[a], ub = C.ub[a];
+    if (lb > -1e300) { const double sl = W.x[gi] - lb; gb -= mu / sl; sg += W.zL[gi] / sl; }
+    if (ub < 1e300) { const double su = ub - W.x[gi]; gb += mu / su; sg += W.zU[gi] / su; }
+    const int ya = yidx(a);
+    if (ya >= 0) { const double* rec = W.rec + (size_t)k * R_SIZE; gb += mu * rec[R_GJ1 + ya] + rec[R_GJ2 + ya]; }
+    W.gh[gi] = gb;
+    W.sig[gi] = sg;
   }
   BMPC_SYNC();
+}
+
+// S.M += W~_kk + delta_w I, added block by block from the stage records (the 44 x 44 block is never
+// stored): joint-variable block (um, q, dq, ddq)^2 = expansion of the 7 x 7 kinematic curvature
+// matrices through the integrator, the 8 x 8 y-block, the remaining diagonal and the
+// velocity / acceleration tracking cross terms.  Every entry of S.M is touched by at most one item.
+constexpr int W_ITEMS = 784 + 64 + 8 + 24;
+BMPC_DEV void add_W(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
+  const double* rec = W.rec + (size_t)k * R_SIZE;
+  const double* rn = rec + R_SIZE;
+  const double* sg = W.sig + NX * k;
+  const bool has_next = k + 1 < C.N;
+  PAR_FOR(it, W_ITEMS) {
+    if (it < 784) {
+      const int ta = it / 196, r1 = it - 196 * ta, i = r1 / 28, r2 = r1 - 28 * i, tb = r2 / 7, j = r2 - 7 * tb;
+      const int a = joff(ta) + i, b = joff(tb) + j;
+      double v = 0.0;
+      if (ta == 0 && tb == 0)
+        v = S.alc[4] * S.alc[4] * rec[R_HQQN + i * 7 + j] + S.alc[4] * S.bec[4] * (rec[R_HQDN + i * 7 + j] + rec[R_HQDN + j * 7 + i]);
+      if (has_next) {
+        v += S.alc[ta] * S.alc[tb] * rn[R_HQQN + i * 7 + j] + S.alc[ta] * S.bec[tb] * rn[R_HQDN + i * 7 + j] +
+             S.bec[ta] * S.alc[tb] * rn[R_HQDN + j * 7 + i];
+        if (ta == 1 && tb == 1) v += rn[R_HQQK + i * 7 + j];
+        if (ta == 1 && tb == 2) v += rn[R_HQDK + i * 7 + j];
+        if (ta == 2 && tb == 1) v += rn[R_HQDK + j * 7 + i];
+      }
+      if (a == b) v += wdiag_const(kc, rec, a, has_next) + sg[a] + delta_w;
+      S.M[a * LDM + b] += v;
+    } else if (it < 848) {
+      const int q = it - 784, ya = q >> 3, yb = q & 7, a = yrow(ya), b = yrow(yb);
+      double v = rec[R_HYB + q];
+      if (a == b) v += sg[a] + delta_w;
+      S.M[a * LDM + b] += v;
+    } else if (it < 856) {
+      const int q = it - 848, a = q == 0 ? oUPHI : (q == 7 ? oDDPHI : oVLIN + q - 1);
+      S.M[a * LDM + a] += wdiag_const(kc, rec, a, has_next) + sg[a] + delta_w;
+    } else {
+      const int q = it - 856, wh = q / 6, m = q - 6 * wh;
+      const double v = (wh < 2 ? -2 * kc.w2 : -2 * kc.w5 * kc.idt) * rec[R_DPD + m];
+      const int a = oVLIN + m, b = wh < 2 ? oDPHI : oDDPHI;
+      if (wh & 1) S.M[b * LDM + a] += v; else S.M[a * LDM + b] += v;
+    }
+  }
 }
 
 // 8 x 8 Cholesky factor of Q_uu in registers; Lr holds L with the RECIPROCAL diagonal.  Every thread
@@ -215,10 +263,8 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 // from the tcr / tcc tables in the tile epilogues.
 BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
-  const double* Wd = W.Wd + (size_t)k * NX * NX;
-  const double* OUa = W.OUa + (size_t)k * NU * NX;
   const bool first = k == 0;      // stage 0: the previous block is fixed -> only the u-columns
-  PAR_FOR(i, NX * NX) S.M[i] += Wd[i] + ((i % (NX + 1)) == 0 ? delta_w : 0.0);
+  add_W(cx, C, W, kc, S, k, delta_w);
   PAR_FOR(i, NK * NZ) S.GK[i] = rec[R_GK + i];
   PAR_FOR(i, NX) S.mv[i] = W.gh[NX * k + i] + S.pv[i];
   PAR_FOR(i, NE) S.cv[i] = W.c[NE * k + i];
@@ -267,7 +313,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
 #pragma unroll
                  for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + NX + j];
                  if (a < NX) {
-                   v += S.YZ[j * LDY + a] + OUa[j * NX + a];
+                   v += S.YZ[j * LDY + a] + ou_entry(rec, S.alc, S.bec, j, a);
                    if (a >= oVLIN && a < oVLIN + 6) v += S.GK[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
                  } else {
                    const int i = a - NX;
@@ -364,8 +410,123 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
   return true;
 }
 
-// Backward + forward + adjoint sweeps on the blocks prepared by kkt_build:
-// dx (primal step) and ynew (equality multipliers of the full step).
+// Forward sweep, executed by ONE warp (no CTA barriers inside): du_k = kappa_k + K_k ds_k,
+// dx_{k+1} = G_k (ds_k, du_k) + c_k.  The running (ds, du) vector lives in shared memory.
+BMPC_DEV void forward_sweep(const Ctx& cx, const Config& C, const Work& W, Smem& S) {
+  double* zb = S.YZ;            // [2][64]: z = (ds (44), du (8)) of the current / next stage
+  double* part = S.YZ + 128;    // [32] partial sums
+  LANE_FOR(l, 128) zb[l] = 0.0;
+  BMPC_WSYNC();
+  for (int k = 0; k < C.N; k++) {
+    const double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
+    const double* K = W.Kk + (size_t)k * NU * NX;
+    double* z = zb + 64 * (k & 1);
+    double* zn = zb + 64 * ((k + 1) & 1);
+    double* dw = W.dx + NX * k;
+    LANE_FOR(l, 32) {           // lane -> (row i of K, quarter of the columns)
+      const int i = l >> 2, c0 = 11 * (l & 3);
+      double a = 0.0;
+      if (k > 0) {
+#pragma unroll
+        for (int j = 0; j < 11; j++) a += K[i * NX + c0 + j] * z[c0 + j];
+      }
+      part[l] = a;
+    }
+    BMPC_WSYNC();
+    LANE_FOR(i, NU) {
+      const double du = W.kap[k * NU + i] + ((part[4 * i] + part[4 * i + 1]) + (part[4 * i + 2] + part[4 * i + 3]));
+      z[NX + i] = du; zn[i] = du; dw[i] = du;
+    }
+    BMPC_WSYNC();
+    LANE_FOR(l, 24) {           // lane -> (kinematic row r, half of the columns)
+      const int r = l % 12, c0 = 26 * (l / 12);
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < 26; j++) a += GK[r * NZ + c0 + j] * z[c0 + j];
+      part[l] = a;
+    }
+    BMPC_WSYNC();
+    LANE_FOR(i, NE) {
+      double v = W.c[NE * k + i];
+      if (i >= rKIN && i < rKIN + NK) v += part[i - rKIN] + part[i - rKIN + 12];
+      else v += G_vec(C, nullptr, z, z + NX, i);
+      zn[8 + i] = v; dw[8 + i] = v;
+    }
+    BMPC_WSYNC();
+  }
+}
+
+// Right-hand side of the adjoint recursion for the equality multipliers, all stages in parallel:
+//   r_k = [W~_kk dw_k + O_k dw_{k-1} + O_{k+1}^T dw_{k+1} + g^_k]_x
+// with the products taken block by block from the stage records (see add_W).  The curvature part
+// uses d q_n = dw_{k+1}[q] - c_{k+1}[q rows] (the linearised change of the integrated state).
+BMPC_DEV void adjoint_rhs(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, const Smem& S, double delta_w) {
+  const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
+  PAR_FOR(it, C.N * NE) {
+    const int k = it / NE, r = 8 + it - NE * k;
+    const bool has_next = k + 1 < C.N;
+    const double* rec = W.rec + (size_t)k * R_SIZE;
+    const double* rn = rec + R_SIZE;
+    const double* dw = W.dx + NX * k;
+    const double* dwp = dw - NX;
+    const double* dwn = dw + NX;
+    double a = W.gh[NX * k + r] + (delta_w + W.sig[NX * k + r] + wdiag_const(kc, rec, r, has_next)) * dw[r];
+    const int ya = yidx(r);
+    if (ya >= 0) {
+#pragma unroll
+      for (int yb = 0; yb < 8; yb++) a += rec[R_HYB + ya * 8 + yb] * dw[yrow(yb)];
+    }
+    if (r >= oVLIN && r < oVLIN + 6) {
+      const int m = r - oVLIN;
+      a += -2 * kc.w2 * rec[R_DPD + m] * dw[oDPHI] - 2 * kc.w5 * kc.idt * rec[R_DPD + m] * dw[oDDPHI];
+      if (k > 0) a += ovv * dwp[r];
+      if (has_next) a += ovv * dwn[r] + 2 * kc.w5 * rn[R_DPD + m] * kc.idt * dwn[oDDPHI];
+    }
+    if (r == oDPHI) for (int m = 0; m < 6; m++) a += -2 * kc.w2 * rec[R_DPD + m] * dw[oVLIN + m];
+    if (r == oDDPHI) {
+      for (int m = 0; m < 6; m++) a += -2 * kc.w5 * kc.idt * rec[R_DPD + m] * dw[oVLIN + m];
+      if (k > 0) for (int m = 0; m < 6; m++) a += 2 * kc.w5 * rec[R_DPD + m] * kc.idt * dwp[oVLIN + m];
+    }
+    const int t = jtype(r);
+    if (t > 0 && has_next) {
+      const int i = jidx(r);
+      const double* cn = W.c + NE * (k + 1);
+      double hq = 0.0, hd = 0.0, hk = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; j++) {
+        const double dqh = dwn[oQ + j] - cn[j], ddh = dwn[oDQ + j] - cn[7 + j];
+        hq += rn[R_HQQN + i * 7 + j] * dqh + rn[R_HQDN + i * 7 + j] * ddh;
+        hd += rn[R_HQDN + j * 7 + i] * dqh;
+        if (t == 1) hk += rn[R_HQQK + i * 7 + j] * dw[oQ + j] + rn[R_HQDK + i * 7 + j] * dw[oDQ + j];
+        if (t == 2) hk += rn[R_HQDK + j * 7 + i] * dw[oQ + j];
+      }
+      a += S.alc[t] * hq + S.bec[t] * hd + hk;
+    }
+    W.ynew[it] = a;
+  }
+}
+
+// Adjoint recursion y_k = r_k + [A_hat_{k+1}^T y_{k+1}]_x, executed by ONE warp.
+BMPC_DEV void adjoint_sweep(const Ctx& cx, const Config& C, const Work& W, Smem& S) {
+  double* yb = S.YZ;            // [2][40]
+  const int N = C.N;
+  LANE_FOR(i, NE) yb[40 * ((N - 1) & 1) + i] = W.ynew[NE * (N - 1) + i];
+  BMPC_WSYNC();
+  for (int k = N - 2; k >= 0; k--) {
+    const double* GKn = W.rec + (size_t)(k + 1) * R_SIZE + R_GK;
+    const double* yn = yb + 40 * ((k + 1) & 1);
+    double* yc = yb + 40 * (k & 1);
+    LANE_FOR(i, NE) {
+      const double v = W.ynew[NE * k + i] + GT_tab(S, GKn, yn, 8 + i);
+      W.ynew[NE * k + i] = v;
+      yc[i] = v;
+    }
+    BMPC_WSYNC();
+  }
+}
+
+// Backward + forward + adjoint sweeps: dx (primal step) and ynew (equality multipliers of the full
+// step).  kkt_prepare must have run for the current iterate.
 BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
   const KktCoef kc = kkt_coef(C, p);
   PAR_FOR(i, NX * NX) S.M[i] = 0.0;
@@ -373,50 +534,12 @@ BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const dou
   BMPC_SYNC();
   for (int k = C.N - 1; k >= 0; k--)
     if (!riccati_stage(cx, C, W, kc, S, k, delta_w)) return false;
-  // forward sweep
-  for (int k = 0; k < C.N; k++) {
-    const double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
-    const double* K = W.Kk + (size_t)k * NU * NX;
-    const double* dsv = k > 0 ? W.dx + NX * (k - 1) : nullptr;
-    double* dw = W.dx + NX * k;
-    PAR_FOR(i, NU) {
-      double a = W.kap[k * NU + i];
-      if (dsv) for (int j = 0; j < NX; j++) a += K[i * NX + j] * dsv[j];
-      dw[i] = a;
-    }
-    BMPC_SYNC();
-    PAR_FOR(i, NE) dw[8 + i] = G_vec(C, GK, dsv, dw, i) + W.c[NE * k + i];
-    BMPC_SYNC();
-  }
-  // adjoint sweep for the equality multipliers:
-  //   y_k = [W~_kk dw_k + O_k dw_{k-1} + O_{k+1}^T dw_{k+1} + g^_k]_x + [A_hat_{k+1}^T y_{k+1}]_x
-  const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
-  for (int k = C.N - 1; k >= 0; k--) {
-    const bool has_next = k + 1 < C.N;
-    const double* Wd = W.Wd + (size_t)k * NX * NX;
-    const double* OUn = W.OUa + (size_t)(k + 1) * NU * NX;
-    const double* dw = W.dx + NX * k;
-    const double* dwp = k > 0 ? W.dx + NX * (k - 1) : nullptr;
-    const double* dwn = has_next ? W.dx + NX * (k + 1) : nullptr;
-    const double* GKn = W.rec + (size_t)(k + 1) * R_SIZE + R_GK;
-    const double* reck = W.rec + (size_t)k * R_SIZE;
-    PAR_FOR(i, NE) {
-      const int r = 8 + i;
-      double a = W.gh[NX * k + r] + delta_w * dw[r];
-      for (int j = 0; j < NX; j++) a += Wd[r * NX + j] * dw[j];
-      if (dwp) {   // O_k rows v, ddphi
-        if (r >= oVLIN && r < oVLIN + 6) a += ovv * dwp[r];
-        if (r == oDDPHI) for (int m = 0; m < 6; m++) a += 2 * kc.w5 * reck[R_DPD + m] * kc.idt * dwp[oVLIN + m];
-      }
-      if (has_next) {
-        for (int q = 0; q < 7; q++) a += OUn[q * NX + r] * dwn[q];                                   // O_u,k+1^T du_{k+1}
-        if (r >= oVLIN && r < oVLIN + 6) a += ovv * dwn[r] + 2 * kc.w5 * reck[R_SIZE + R_DPD + (r - oVLIN)] * kc.idt * dwn[oDDPHI];
-        a += GT_vec(C, GKn, W.ynew + NE * (k + 1), r);
-      }
-      W.ynew[NE * k + i] = a;
-    }
-    BMPC_SYNC();
-  }
+  if (ctx_warp(cx) == 0) forward_sweep(cx, C, W, S);
+  BMPC_SYNC();
+  adjoint_rhs(cx, C, W, kc, S, delta_w);
+  BMPC_SYNC();
+  if (ctx_warp(cx) == 0) adjoint_sweep(cx, C, W, S);
+  BMPC_SYNC();
   return true;
 }
 
