@@ -14,11 +14,15 @@
 
 #ifdef BMPC_HOST_EMU
 #define BMPC_DEV inline
+#define BMPC_NOINLINE inline
 #define BMPC_HD inline
 #define BMPC_SYNC() ((void)0)
 #define BMPC_LDG(ptr) (*(ptr))
 #else
 #define BMPC_DEV __device__ __forceinline__
+// large phase bodies exist once in the kernel image (the interior-point loop has to stay resident in
+// the instruction cache; everything force-inlined was 435 KB of SASS)
+#define BMPC_NOINLINE __device__ __noinline__
 #define BMPC_HD __host__ __device__ inline
 #define BMPC_SYNC() __syncthreads()
 #define BMPC_LDG(ptr) __ldg(ptr)
@@ -29,19 +33,32 @@
 #ifdef BMPC_HOST_EMU
 #define LANE_FOR(l, n) for (int l = 0; l < (n); l++)
 #define BMPC_WSYNC() ((void)0)
+// items of a phase dealt to the threads of warps [w0, w1) only (other warps skip the loop)
+#define ROLE_FOR(i, n, w0, w1) for (int i = 0; i < (n); i++)
 #else
 #define LANE_FOR(l, n) for (int l = (cx.tid & 31); l < (n); l += 32)
 #define BMPC_WSYNC() __syncwarp()
+#define ROLE_FOR(i, n, w0, w1) \
+  for (int i = ((cx.tid >> 5) >= (w0) && (cx.tid >> 5) < (w1)) ? cx.tid - 32 * (w0) : (n); i < (n); i += 32 * ((w1) - (w0)))
 #endif
 
 namespace bmpc {
 
 struct Ctx {
   int tid, nt;
-  double* red;  // shared scratch for block reductions (8 x 32 doubles)
+  double* red;  // shared scratch for block reductions (8 values x 8 warps)
 };
 BMPC_DEV int ctx_warp(const Ctx& cx) { return cx.tid >> 5; }
 BMPC_DEV int ctx_nwarps(const Ctx& cx) { return (cx.nt + 31) >> 5; }
+// is this thread in warps [w0, w1)?  (host emulation: the single thread plays every role)
+BMPC_DEV bool in_role(const Ctx& cx, int w0, int w1) {
+#ifdef BMPC_HOST_EMU
+  (void)cx; (void)w0; (void)w1;
+  return true;
+#else
+  return (cx.tid >> 5) >= w0 && (cx.tid >> 5) < w1;
+#endif
+}
 
 // One 8 x 8 output tile of a matrix product on the FP64 tensor-core path, executed by one warp:
 //   C(r, c) = sum_{kk < 4 ksteps} a(r, kk) * b(kk, c),   r, c in 0..7,
@@ -69,6 +86,42 @@ BMPC_DEV void mma_tile(const Ctx& cx, int ksteps, FA a, FB b, FE epi) {
   }
   epi(r, 2 * q, c0);
   epi(r, 2 * q + 1, c1);
+#endif
+}
+// Row block of tiles that share their A fragments: for t < nt (<= NT)
+//   C_t(r, c) = cin(t, r, c) + sum_{kk < 4 KS} a(r, kk) * b(t, kk, c),
+// executed by one warp; the A fragments are loaded once, C starts from cin (a previous pass) and
+// every element is handed to epi(t, r, c, value) exactly once.
+template <int KS, int NT, class FA, class FB, class FC, class FE>
+BMPC_DEV void mma_rowblock(const Ctx& cx, int nt, FA a, FB b, FC cin, FE epi) {
+#ifdef BMPC_HOST_EMU
+  (void)cx;
+  for (int t = 0; t < nt; t++)
+    for (int r = 0; r < 8; r++)
+      for (int c = 0; c < 8; c++) {
+        double v = cin(t, r, c);
+        for (int kk = 0; kk < 4 * KS; kk++) v += a(r, kk) * b(t, kk, c);
+        epi(t, r, c, v);
+      }
+#else
+  const int lane = cx.tid & 31, r = lane >> 2, q = lane & 3;
+  double av[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) av[ks] = a(r, 4 * ks + q);
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t < nt) {
+      double c0 = cin(t, r, 2 * q), c1 = cin(t, r, 2 * q + 1);
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        const double bv = b(t, 4 * ks + q, r);
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(av[ks]), "d"(bv));
+      }
+      epi(t, r, 2 * q, c0);
+      epi(t, r, 2 * q + 1, c1);
+    }
+  }
 #endif
 }
 // tiles of a phase are dealt to the warps of the CTA round-robin
@@ -153,7 +206,8 @@ enum {
   R_HYB = R_COST + 2,      // [8][8] y-block (p_pos, p_rot, phi, dphi) of W~: HY + z.HD + J_d^T Sigma_s J_d + dphi tracking term
   R_GJ1 = R_HYB + 64,      // [8] sum_r JD_r / s_r              (multiplied by mu in g^)
   R_GJ2 = R_GJ1 + 8,       // [8] sum_r JD_r Sigma_r (d_r + s_r)
-  R_SIZE = R_GJ2 + 8
+  R_SIG = R_GJ2 + 8,       // [3][12] Sigma_r = z_r / s_r, 1 / s_r, Sigma_r (d_r + s_r)
+  R_SIZE = R_SIG + 3 * ND
 };
 // forward-kinematics scratch of one chain evaluation
 enum {
@@ -163,10 +217,16 @@ enum {
   F_OT = F_W + 21,         // [7][3] sum_{k>i} dq_k z_k
   F_OH = F_OT + 21,        // [8][3] sum_{k<i} dq_k z_k   (entry 7 = total angular velocity)
   F_POS = F_OH + 24,       // [3]
-  F_Q = F_POS + 3,         // [7] joint angles of this evaluation
-  F_DQ = F_Q + 7,          // [7]
-  F_SIZE = F_DQ + 8
+  F_SN = F_POS + 3,        // [7] sin / cos of the joint angles of this evaluation
+  F_CS = F_SN + 7,         // [7]
+  F_DQ = F_CS + 7,         // [7]
+  F_SIZE = F_DQ + 7
 };
+
+// one copy each of the transcendental routines
+BMPC_NOINLINE double bmpc_log(double v) { return log(v); }
+BMPC_NOINLINE double bmpc_exp(double v) { return exp(v); }
+BMPC_DEV double bmpc_pow(double v, double e) { return bmpc_exp(e * bmpc_log(v)); }   // v > 0
 
 BMPC_DEV void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
@@ -178,35 +238,39 @@ BMPC_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[
 // ---- block reductions: result is returned to every thread ------------------------------------
 enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
 
-template <int K>
-BMPC_DEV void block_reduce(const Ctx& cx, double (&v)[K], const int (&op)[K]) {
+// (one copy in the kernel image: K and the operations are run-time arguments)
+BMPC_NOINLINE void block_reduce_n(const Ctx& cx, double* v, const int* op, int K) {
 #ifndef BMPC_HOST_EMU
   const int lane = cx.tid & 31, warp = cx.tid >> 5, nw = (cx.nt + 31) >> 5;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < K; k++) {
     double a = v[k];
-#pragma unroll
+    const int o_ = op[k];
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
       double b = __shfl_xor_sync(0xffffffffu, a, o);
-      a = op[k] == RED_SUM ? a + b : (op[k] == RED_MAX ? fmax(a, b) : fmin(a, b));
+      a = o_ == RED_SUM ? a + b : (o_ == RED_MAX ? fmax(a, b) : fmin(a, b));
     }
-    if (lane == 0) cx.red[k * 32 + warp] = a;
+    if (lane == 0) cx.red[k * 8 + warp] = a;
   }
   __syncthreads();
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < K; k++) {
-    double a = cx.red[k * 32];
+    double a = cx.red[k * 8];
+    const int o_ = op[k];
     for (int w = 1; w < nw; w++) {
-      double b = cx.red[k * 32 + w];
-      a = op[k] == RED_SUM ? a + b : (op[k] == RED_MAX ? fmax(a, b) : fmin(a, b));
+      double b = cx.red[k * 8 + w];
+      a = o_ == RED_SUM ? a + b : (o_ == RED_MAX ? fmax(a, b) : fmin(a, b));
     }
     v[k] = a;
   }
   __syncthreads();
 #else
-  (void)cx; (void)v; (void)op;
+  (void)cx; (void)v; (void)op; (void)K;
 #endif
 }
+template <int K>
+BMPC_DEV void block_reduce(const Ctx& cx, double (&v)[K], const int (&op)[K]) { block_reduce_n(cx, v, op, K); }
 
 // status codes returned per instance
 enum { ST_SUCCESS = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_NUMERIC = 4 };

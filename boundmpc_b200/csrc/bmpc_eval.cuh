@@ -20,7 +20,7 @@ BMPC_DEV void eval_instance(const Ctx& cx, const Config& C, const Work& W, Smem&
   PAR_FOR(i, ND * N) { const int k = i / ND, r = i - ND * k; W.zs[i] = io.lam ? io.lam[(NE + ND) * k + NE + r] : 0.0; W.s[i] = 1.0; }
   BMPC_SYNC();
   eval_full(cx, C, W, io.p, W.x);
-  phase_path<2>(cx, C, W, io.p, W.x, W.dtr, W.st);
+  phase_path(cx, C, W, io.p, W.x, W.dtr, W.st, 2);
   BMPC_SYNC();
   if (io.f && cx.tid == 0) { double f = 0; for (int k = 0; k < N; k++) f += W.cost[k]; *io.f = f; }
   if (io.g) PAR_FOR(i, NG * N) { const int k = i / NG, r = i - NG * k; io.g[i] = r < NE ? W.c[NE * k + r] : W.st[NQ * k + r - NE]; }
@@ -62,7 +62,7 @@ BMPC_DEV void eval_instance(const Ctx& cx, const Config& C, const Work& W, Smem&
         PAR_FOR(i, NX * NX) {
           const int a = i / NX, b = i - NX * a;   // row in w_k, col in w_{k-1}
           double v = 0.0;
-          if (a < 8) v = ou_entry(rec, al, be, a, b);
+          if (a < 8) v = ou_entry(rec + R_HQQN, al, be, a, b);
           else if (a >= oVLIN && a < oVLIN + 6 && b == a) v = ovv;
           else if (a == oDDPHI && b >= oVLIN && b < oVLIN + 6) v = 2 * kc.w5 * rec[R_DPD + b - oVLIN] * kc.idt;
           io.hess[(size_t)(NX * k + a) * n + NX * (k - 1) + b] = v;

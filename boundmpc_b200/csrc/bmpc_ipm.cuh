@@ -119,7 +119,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
     for (;;) {
       const double emu = fmax(dinf / sd, fmax(pinf, fmax(szmax - mu, mu - szmin) / sc));
       if (!(mu > C.tol / 10 && emu <= C.kappa_eps * mu)) break;
-      mu = fmax(C.tol / 10, fmin(C.kappa_mu * mu, pow(mu, C.theta_mu)));
+      mu = fmax(C.tol / 10, fmin(C.kappa_mu * mu, bmpc_pow(mu, C.theta_mu)));
       mu_changed = true;
     }
     if (mu_changed) { if (cx.tid == 0) S.flag[1] = 0; BMPC_SYNC(); }
@@ -155,7 +155,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       if (dsv < 0) sv4[0] = fmin(sv4[0], -tau * sv / dsv);
       if (dzv < 0) sv4[1] = fmin(sv4[1], -tau * zv / dzv);
       sv4[2] -= mu * dsv / sv;
-      sv4[3] -= mu * log(sv);
+      sv4[3] -= mu * bmpc_log(sv);
     }
     PAR_FOR(i, n) {
       const int a = i % NX;
@@ -168,7 +168,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
         if (dxi < 0) sv4[0] = fmin(sv4[0], -tau * sl / dxi);
         if (dl < 0) sv4[1] = fmin(sv4[1], -tau * z / dl);
         sv4[2] -= mu * dxi / sl;
-        sv4[3] -= mu * log(sl);
+        sv4[3] -= mu * bmpc_log(sl);
       }
       if (u < 1e300) {
         const double su = u - W.x[i], z = W.zU[i];
@@ -176,7 +176,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
         if (dxi > 0) sv4[0] = fmin(sv4[0], tau * su / dxi);
         if (du < 0) sv4[1] = fmin(sv4[1], -tau * z / du);
         sv4[2] += mu * dxi / su;
-        sv4[3] -= mu * log(su);
+        sv4[3] -= mu * bmpc_log(su);
       }
       W.dzL[i] = dl; W.dzU[i] = du;
     }
@@ -196,12 +196,12 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       eval_values(cx, C, W, p, W.xt, W.ct, W.dtr);
       double tv2[2] = {0.0, 0.0};   // theta_trial, phi_trial
       PAR_FOR(i, ne) tv2[0] += fabs(W.ct[i]);
-      PAR_FOR(i, nd) { tv2[0] += fabs(W.dtr[i] + W.st[i]); tv2[1] -= mu * log(W.st[i]); }
+      PAR_FOR(i, nd) { tv2[0] += fabs(W.dtr[i] + W.st[i]); tv2[1] -= mu * bmpc_log(W.st[i]); }
       PAR_FOR(i, n) {
         const int a = i % NX;
         const double l = C.lb[a], u = C.ub[a];
-        if (l > -1e300) tv2[1] -= mu * log(W.xt[i] - l);
-        if (u < 1e300) tv2[1] -= mu * log(u - W.xt[i]);
+        if (l > -1e300) tv2[1] -= mu * bmpc_log(W.xt[i] - l);
+        if (u < 1e300) tv2[1] -= mu * bmpc_log(u - W.xt[i]);
       }
       PAR_FOR(k, N) tv2[1] += W.cost[k];
       {
@@ -214,7 +214,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       for (int q = 0; q < nfilt; q++)
         if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }
       if (!filt_ok) continue;
-      const bool sw = dphi < 0 && alpha * pow(-dphi, C.s_phi) > pow(th_cur, C.s_theta);
+      const bool sw = dphi < 0 && alpha * bmpc_pow(-dphi, C.s_phi) > (th_cur > 0 ? bmpc_pow(th_cur, C.s_theta) : 0.0);
       if (th_cur <= theta_min && sw) {
         if (ph_t <= phi_cur + C.eta_phi * alpha * dphi) { accepted = true; ftype = true; break; }
       } else {
@@ -259,7 +259,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
 
   // ---- report in the reference's conventions: x, g, lam_g, lam_x (CasADi: L = f + lam_g.g + lam_x.x)
   BMPC_SYNC();
-  phase_path<2>(cx, C, W, p, W.x, W.dtr, W.st);   // W.st[0..7N) <- reference-form rows 36..42
+  phase_path(cx, C, W, p, W.x, W.dtr, W.st, 2);   // W.st[0..7N) <- reference-form rows 36..42
   BMPC_SYNC();
   PAR_FOR(i, n) {
     io.x[i] = W.x[i];

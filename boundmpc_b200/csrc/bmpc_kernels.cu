@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, unsigned int*);
 struct SolveVariant { int threads, minb; solve_fn fn; };
 static const SolveVariant kVariants[] = {
-    {128, 3, k_solve<128, 3>}, {128, 4, k_solve<128, 4>}, {256, 1, k_solve<256, 1>}, {256, 2, k_solve<256, 2>},
+    {128, 3, k_solve<128, 3>}, {192, 2, k_solve<192, 2>}, {256, 1, k_solve<256, 1>}, {256, 2, k_solve<256, 2>},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 

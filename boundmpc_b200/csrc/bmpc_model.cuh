@@ -103,8 +103,13 @@ BMPC_DEV void phase_integrate(const Ctx& cx, const Config& C, const Work& W, con
       c[NE * k + 14 + j] = ddqn - w[oDDQ + j];
       double* f0 = W.fk + (size_t)(2 * k) * F_SIZE;
       double* f1 = f0 + F_SIZE;
-      f0[F_Q + j] = qn; f0[F_DQ + j] = dqn;
-      f1[F_Q + j] = q; f1[F_DQ + j] = dq;
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {   // (one copy of sincos)
+        double sn, cs;
+        sincos(h ? q : qn, &sn, &cs);
+        double* f = h ? f1 : f0;
+        f[F_SN + j] = sn; f[F_CS + j] = cs; f[F_DQ + j] = h ? dq : dqn;
+      }
     } else {
       const double ph = wp[oPHI], dph = wp[oDPHI], ddph = wp[oDDPHI], um = wp[oUPHI], u = w[oUPHI];
       c[NE * k + 33] = ph + C.a_dq * dph + C.a_ddq * ddph + C.a_um * um + C.a_u * u - w[oPHI];
@@ -117,7 +122,7 @@ BMPC_DEV void phase_integrate(const Ctx& cx, const Config& C, const Work& W, con
 // Phase 2: forward kinematics of one chain evaluation (one thread per chain):
 // joint axes z_i, lever arms r_i = p - o_i and the running sums needed by the derivative
 // formulas.  `tails` = false skips W / OT (values-only evaluation of the omega(q_k) chain).
-BMPC_DEV void fk_chain(double* f) {
+BMPC_NOINLINE void fk_chain(double* f) {
   double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   double o[3] = {0, 0, 0};
   double org[7][3], z[7][3], dq[7];
@@ -128,8 +133,7 @@ BMPC_DEV void fk_chain(double* f) {
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) Rn[i][j] = R[i][0] * kJROT[k][0][j] + R[i][1] * kJROT[k][1][j] + R[i][2] * kJROT[k][2][j];
     for (int i = 0; i < 3; i++) { z[k][i] = Rn[i][2]; org[k][i] = o[i]; }
-    double sn, cs;
-    sincos(f[F_Q + k], &sn, &cs);
+    const double sn = f[F_SN + k], cs = f[F_CS + k];
     dq[k] = f[F_DQ + k];
     for (int i = 0; i < 3; i++) {
       R[i][0] = Rn[i][0] * cs + Rn[i][1] * sn;
@@ -162,7 +166,7 @@ BMPC_DEV void fk_chain(double* f) {
 }
 
 BMPC_DEV void phase_fk(const Ctx& cx, const Config& C, const Work& W) {
-  PAR_FOR(it, 2 * C.N) fk_chain(W.fk + (size_t)it * F_SIZE);
+  ROLE_FOR(it, 2 * C.N, 0, 1) fk_chain(W.fk + (size_t)it * F_SIZE);
 }
 
 // Phase 3a: kinematic residual rows 21..32 (casadi_ocp_formulation.py:284-291,
@@ -221,9 +225,8 @@ BMPC_DEV void blend_terms(double wgt, const double* a, const double (*A)[7], con
   }
 }
 
-template <int MODE>
-BMPC_DEV void path_stage(const Config& C, const double* p, const double* wp, const double* w, double* rec, double* dout,
-                         double* cost_out, double* gq, const double* sk = nullptr, const double* zk = nullptr) {
+BMPC_NOINLINE void path_stage(const int MODE, const Config& C, const double* p, const double* wp, const double* w, double* rec, double* dout,
+                              double* cost_out, double* gq, const double* sk, const double* zk) {
   const PLayout& L = C.L;
   const int S = L.S;
   const double phi = w[oPHI], dphi = w[oDPHI], ddphi = w[oDDPHI];
@@ -295,8 +298,7 @@ BMPC_DEV void path_stage(const Config& C, const double* p, const double* wp, con
   const double w10 = BMPC_LDG(wt + 10), w11 = BMPC_LDG(wt + 11), w12 = BMPC_LDG(wt + 12), w13 = BMPC_LDG(wt + 13);
   const double arg = 100.0 * (phi - (BMPC_LDG(p + L.phimax) - 0.02));
   double sg;
-  if (arg >= 0) { const double e = exp(-arg); sg = 1.0 / (1.0 + e); }
-  else { const double e = exp(arg); sg = e / (1.0 + e); }
+  { const double e = bmpc_exp(-fabs(arg)); sg = arg >= 0 ? 1.0 / (1.0 + e) : e / (1.0 + e); }
   const double sg1 = 100.0 * sg * (1.0 - sg), sg2 = 100.0 * sg1 * (1.0 - 2.0 * sg);
   double cost = 0.0;
   double ev[6], fv[6];
@@ -393,38 +395,51 @@ BMPC_DEV void path_stage(const Config& C, const double* p, const double* wp, con
   for (int i = 0; i < 7; i++) rec[R_GY + i] = GY[i];
   for (int i = 0; i < 49; i++) rec[R_HY + i] = HY[i];
   rec[R_COST] = cost;
-  // y-block of the condensed Hessian and the slack part of g^ (Sigma_r = z_r / s_r)
-  {
-    const double* JD = rec + R_JD;
-    double nd = 0.0, zh = 0.0;
-    for (int m = 0; m < 6; m++) nd += dpd[m] * dpd[m];
-    double sig[ND], c1[ND], c2[ND];
-    for (int r = 0; r < ND; r++) {
-      const double sv = sk[r], zv = zk[r];
-      sig[r] = zv / sv; c1[r] = 1.0 / sv; c2[r] = sig[r] * (dout[r] + sv);
-      zh += zv * rec[R_HD + r];
-    }
-    for (int a = 0; a < 8; a++) {
-      double g1 = 0.0, g2 = 0.0;
-      for (int r = 0; r < ND; r++) { g1 += JD[r * 8 + a] * c1[r]; g2 += JD[r * 8 + a] * c2[r]; }
-      rec[R_GJ1 + a] = g1; rec[R_GJ2 + a] = g2;
-      for (int b = 0; b < 8; b++) {
-        double v = (a < 7 && b < 7) ? HY[a * 7 + b] : 0.0;
-        for (int r = 0; r < ND; r++) v += sig[r] * JD[r * 8 + a] * JD[r * 8 + b];
-        if (a == 6 && b == 6) v += zh;
-        if (a == 7 && b == 7) v += 2 * w2 * nd + 2 * w7;
-        rec[R_HYB + a * 8 + b] = v;
-      }
-    }
+  for (int r = 0; r < ND; r++) {   // slack terms for phase_path_blocks: Sigma_r, 1 / s_r, Sigma_r (d_r + s_r)
+    const double sv = sk[r], sgm = zk[r] / sv;
+    rec[R_SIG + r] = sgm; rec[R_SIG + ND + r] = 1.0 / sv; rec[R_SIG + 2 * ND + r] = sgm * (dout[r] + sv);
   }
   *cost_out = cost;
 }
 
-template <int MODE>
-BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq) {
-  PAR_FOR(k, C.N) {
-    path_stage<MODE>(C, p, prev_block(W, x, k), x + NX * k, W.rec + (size_t)k * R_SIZE, d + ND * k, W.cost + k,
-                     MODE == 2 ? gq + NQ * k : nullptr, W.s + ND * k, W.zs + ND * k);
+// One item per stage, dealt to the lanes of warp `w` (long serial items: they run next to the
+// forward-kinematics chains of warp 0 instead of after them).
+BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq, int mode, int w = 0) {
+  ROLE_FOR(k, C.N, w, w + 1) {
+    path_stage(mode, C, p, prev_block(W, x, k), x + NX * k, W.rec + (size_t)k * R_SIZE, d + ND * k, W.cost + k,
+               mode == 2 ? gq + NQ * k : nullptr, W.s + ND * k, W.zs + ND * k);
+  }
+}
+
+// y-block of the condensed Hessian, HYB = HY + z.HD + J_d^T Sigma_s J_d + dphi tracking term, and the
+// slack part of g^ (Sigma_r = z_r / s_r); 80 independent items per stage, run after path_stage<1>.
+BMPC_DEV void phase_path_blocks(const Ctx& cx, const Config& C, const Work& W, const double* p) {
+  const double w2 = BMPC_LDG(p + C.L.w + 2), w7 = BMPC_LDG(p + C.L.w + 7);
+  PAR_FOR(it, C.N * 80) {
+    const int k = it / 80, q = it - 80 * k;
+    double* rec = W.rec + (size_t)k * R_SIZE;
+    const double* JD = rec + R_JD;
+    const double* sg = rec + R_SIG;
+    if (q < 64) {
+      const int a = q >> 3, b = q & 7;
+      double v = (a < 7 && b < 7) ? rec[R_HY + a * 7 + b] : 0.0;
+#pragma unroll
+      for (int r = 0; r < ND; r++) v += sg[r] * JD[r * 8 + a] * JD[r * 8 + b];
+      if (a == 6 && b == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * rec[R_HD + r];
+      if (a == 7 && b == 7) {
+        double nd = 0.0;
+        for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+        v += 2 * w2 * nd + 2 * w7;
+      }
+      rec[R_HYB + q] = v;
+    } else {
+      const int a = (q - 64) & 7;
+      const double* cf = sg + (q < 72 ? ND : 2 * ND);
+      double g = 0.0;
+#pragma unroll
+      for (int r = 0; r < ND; r++) g += JD[r * 8 + a] * cf[r];
+      rec[(q < 72 ? R_GJ1 : R_GJ2) + a] = g;
+    }
   }
 }
 
@@ -479,14 +494,15 @@ BMPC_DEV void phase_kin_hessian(const Ctx& cx, const Config& C, const Work& W) {
 
 // Phase 5: kinematic rows of [A_hat | B] (first derivatives).  One item per (stage, joint).
 //   d pos / dq_i = z_i x r_i ;  d(Jv dq)/dq_i = z_i x W_i + Om_{<i} x (z_i x r_i) ;  d(Jw dq)/dq_i = z_i x Om_{>i}
-BMPC_DEV void phase_kin_jacobian(const Ctx& cx, const Config& C, const Work& W) {
-  PAR_FOR(it, C.N * NZ) {   // zero fill + identity of the p_rot columns
+BMPC_DEV void phase_kin_jacobian_init(const Ctx& cx, const Config& C, const Work& W) {
+  ROLE_FOR(it, C.N * NZ, 2, ctx_nwarps(cx)) {   // zero fill + identity of the p_rot columns
     const int k = it / NZ, col = it - NZ * k;
     double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
     for (int r = 0; r < NK; r++) GK[r * NZ + col] = 0.0;
     if (col >= oPROT && col < oPROT + 3) GK[(3 + col - oPROT) * NZ + col] = 1.0;
   }
-  BMPC_SYNC();
+}
+BMPC_DEV void phase_kin_jacobian(const Ctx& cx, const Config& C, const Work& W) {
   PAR_FOR(it, C.N * 7) {
     const int k = it / 7, j = it - 7 * k;
     const double* f0 = W.fk + (size_t)(2 * k) * F_SIZE;
@@ -548,26 +564,29 @@ BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const 
 
 // ---------------------------------------------------------------------------------------------
 // Whole-horizon evaluation.  full = derivative records too (needs the current multipliers in W.y).
-BMPC_DEV void eval_values(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* c, double* d) {
+// The two long serial pieces — the kinematic chains (2 N lanes of warp 0) and the path terms (N lanes
+// of warp 1) — run side by side; everything else is dealt to all threads.
+BMPC_NOINLINE void eval_values(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* c, double* d) {
   phase_integrate(cx, C, W, x, c);
   BMPC_SYNC();
   phase_fk(cx, C, W);
+  phase_path(cx, C, W, p, x, d, nullptr, 0, 1);
   BMPC_SYNC();
   phase_kin_residual(cx, C, W, x, c);
-  phase_path<0>(cx, C, W, p, x, d, nullptr);
   BMPC_SYNC();
 }
 
-BMPC_DEV void eval_full(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x) {
+BMPC_NOINLINE void eval_full(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x) {
   phase_integrate(cx, C, W, x, W.c);
   BMPC_SYNC();
   phase_fk(cx, C, W);
+  phase_path(cx, C, W, p, x, W.d, nullptr, 1, 1);
+  phase_kin_jacobian_init(cx, C, W);
   BMPC_SYNC();
   phase_kin_residual(cx, C, W, x, W.c);
-  phase_path<1>(cx, C, W, p, x, W.d, nullptr);
   phase_kin_hessian(cx, C, W);
   phase_kin_jacobian(cx, C, W);
-  BMPC_SYNC();
+  phase_path_blocks(cx, C, W, p);
   phase_grad_f(cx, C, W, p, x, W.gradf);
   BMPC_SYNC();
 }

@@ -27,7 +27,10 @@ constexpr int LDY = NZ;        // 52
 constexpr int LDQ = 12;
 struct Smem {
   double M[48 * LDM];          // W~_kk + P_{k+1}, overwritten by P_k
-  double GK[NK * NZ + 4];      // kinematic rows of G_k = [A_hat | B]
+  double GKb[2][NK * NZ + 4];  // kinematic rows of G_k = [A_hat | B]; stage k uses buffer k & 1, the other one is prefetched
+  double Hn[2][4 * 49 + 4];    // HQQN, HQDN, HQQK, HQDK of stage k in buffer k & 1
+  double Hc[64 + 8 + NX];      // current stage only: HYB [64], DPD [6], sig [44]
+  double ghs[NX];              // g^_k
   double YZ[NX * LDY];         // M[:, x] G  (rows 0..7 = u rows "Z", rows 8..43 = x rows "Y")
   double Qu[56 * LDQ];         // columns u_k of Q: rows 0..43 = Q_su, rows 44..51 = Q_uu
   double Ks[NU * NX + 4];      // feedback gain K_k
@@ -41,7 +44,7 @@ struct Smem {
   double tcc[NZ * 3];          // constant rows of G per column: coefficients ...
   int tcr[NZ * 3];             // ... and x-row indices (triv_col as a table)
   double alc[5], bec[5];       // d q_n / d(um, q, dq, ddq, u) and d dq_n / d(...) of the integrator (type_coef)
-  double red[8 * 32];          // block reductions
+  double red[8 * 8];           // block reductions (8 values x up to 8 warps)
   double filt[2 * 64];         // filter entries (theta, phi)
   int flag[4];
 };
@@ -101,7 +104,7 @@ BMPC_DEV int joff(int t) { return t == 0 ? oU : (t == 1 ? oQ : (t == 2 ? oDQ : o
 BMPC_DEV int yrow(int y) { return y < 6 ? oPPOS + y : (y == 6 ? oPHI : oDPHI); }
 
 // constant part of the diagonal of W~_kk (quadratic cost terms, bound_mpc_functions.py:205-246)
-BMPC_DEV double wdiag_const(const KktCoef& kc, const double* rec, int a, bool has_next) {
+BMPC_DEV double wdiag_const(const KktCoef& kc, const double* dpd, int a, bool has_next) {
   if (a < 7) return 2 * kc.w13;
   if (a == 7) return 2 * kc.w9;
   if (a < 15) return 2 * kc.w10;
@@ -110,7 +113,7 @@ BMPC_DEV double wdiag_const(const KktCoef& kc, const double* rec, int a, bool ha
   if (a >= oVLIN && a < oVLIN + 6) return 2 * kc.w2 + 2 * kc.w5 * kc.idt * kc.idt * (has_next ? 2.0 : 1.0);
   if (a == oDDPHI) {
     double nd = 0.0;
-    for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+    for (int m = 0; m < 6; m++) nd += dpd[m] * dpd[m];
     return 2 * kc.w5 * nd + 2 * kc.w8;
   }
   return 0.0;
@@ -121,7 +124,7 @@ BMPC_DEV double wdiag_const(const KktCoef& kc, const double* rec, int a, bool ha
 BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, const double* al, const double* be, int k, int a, int b) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
   const bool has_next = k + 1 < C.N;
-  double v = a == b ? wdiag_const(kc, rec, a, has_next) : 0.0;
+  double v = a == b ? wdiag_const(kc, rec + R_DPD, a, has_next) : 0.0;
   const int ya = yidx(a), yb = yidx(b);
   if (ya >= 0 && yb >= 0) {
     if (ya < 7 && yb < 7) v += rec[R_HY + ya * 7 + yb];
@@ -161,12 +164,12 @@ BMPC_DEV double wd_entry(const Config& C, const Work& W, const KktCoef& kc, cons
 }
 
 // entry (i, col) of the rows u_k of W~_{k,k-1} (kinematic coupling of u_k with (um, q, dq, ddq) of the
-// previous block); al / be may point to the shared tables
-BMPC_DEV double ou_entry(const double* rec, const double* al, const double* be, int i, int col) {
+// previous block); H = HQQN (49) followed by HQDN (49) of stage k; al / be may point to the shared tables
+BMPC_DEV double ou_entry(const double* H, const double* al, const double* be, int i, int col) {
   const int t = jtype(col);
   if (i >= 7 || t < 0) return 0.0;
   const int j = jidx(col);
-  return al[4] * al[t] * rec[R_HQQN + i * 7 + j] + al[4] * be[t] * rec[R_HQDN + i * 7 + j] + be[4] * al[t] * rec[R_HQDN + j * 7 + i];
+  return al[4] * al[t] * H[i * 7 + j] + al[4] * be[t] * H[49 + i * 7 + j] + be[4] * al[t] * H[49 + j * 7 + i];
 }
 
 // Once per interior-point iteration: bound part of the barrier Hessian (W.sig) and the gradient g^ of
@@ -186,48 +189,86 @@ BMPC_DEV void kkt_prepare(const Ctx& cx, const Config& C, const Work& W, double 
   BMPC_SYNC();
 }
 
-// S.M += W~_kk + delta_w I, added block by block from the stage records (the 44 x 44 block is never
-// stored): joint-variable block (um, q, dq, ddq)^2 = expansion of the 7 x 7 kinematic curvature
-// matrices through the integrator, the 8 x 8 y-block, the remaining diagonal and the
-// velocity / acceleration tracking cross terms.  Every entry of S.M is touched by at most one item.
-constexpr int W_ITEMS = 784 + 64 + 8 + 24;
-BMPC_DEV void add_W(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
+// Stage data of the backward sweep is staged in shared memory one stage ahead (stage_prefetch runs
+// in the gain phase of stage k + 1, on the warps that have no column to solve).
+BMPC_DEV void stage_prefetch(const Ctx& cx, const Config& C, const Work& W, Smem& S, int k, int w0, int w1) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
-  const double* rn = rec + R_SIZE;
-  const double* sg = W.sig + NX * k;
+  double* GK = S.GKb[k & 1];
+  double* Hk = S.Hn[k & 1];
+  ROLE_FOR(i, NK * NZ, w0, w1) GK[i] = rec[R_GK + i];
+  ROLE_FOR(i, 4 * 49, w0, w1) Hk[i] = rec[R_HQQN + i];
+  ROLE_FOR(i, 64, w0, w1) S.Hc[i] = rec[R_HYB + i];
+  ROLE_FOR(i, 6, w0, w1) S.Hc[64 + i] = rec[R_DPD + i];
+  ROLE_FOR(i, NX, w0, w1) { S.Hc[72 + i] = W.sig[NX * k + i]; S.ghs[i] = W.gh[NX * k + i]; }
+  ROLE_FOR(i, NE, w0, w1) S.cv[i] = W.c[NE * k + i];
+}
+
+// S.M += W~_kk + delta_w I, added block by block from the staged stage records (the 44 x 44 block is
+// never stored).  Items: 49 index pairs (i, j) of the 7 x 7 kinematic curvature matrices, each expanded
+// through the integrator into the 16 blocks of the joint-variable square (um, q, dq, ddq)^2; the 8 x 8
+// y-block; the remaining diagonal; the velocity / acceleration tracking cross terms.  Every entry of
+// S.M is touched by at most one item.
+constexpr int W_ITEMS = 49 + 64 + 8 + 24;
+BMPC_DEV void add_W(const Ctx& cx, const Config& C, const KktCoef& kc, Smem& S, int k, double delta_w) {
+  const double* Hk = S.Hn[k & 1];          // HQQN 0, HQDN 49, HQQK 98, HQDK 147
+  const double* Hx = S.Hn[(k + 1) & 1];    // same of stage k + 1
+  const double* dpd = S.Hc + 64;
+  const double* sg = S.Hc + 72;
   const bool has_next = k + 1 < C.N;
   PAR_FOR(it, W_ITEMS) {
-    if (it < 784) {
-      const int ta = it / 196, r1 = it - 196 * ta, i = r1 / 28, r2 = r1 - 28 * i, tb = r2 / 7, j = r2 - 7 * tb;
-      const int a = joff(ta) + i, b = joff(tb) + j;
-      double v = 0.0;
-      if (ta == 0 && tb == 0)
-        v = S.alc[4] * S.alc[4] * rec[R_HQQN + i * 7 + j] + S.alc[4] * S.bec[4] * (rec[R_HQDN + i * 7 + j] + rec[R_HQDN + j * 7 + i]);
-      if (has_next) {
-        v += S.alc[ta] * S.alc[tb] * rn[R_HQQN + i * 7 + j] + S.alc[ta] * S.bec[tb] * rn[R_HQDN + i * 7 + j] +
-             S.bec[ta] * S.alc[tb] * rn[R_HQDN + j * 7 + i];
-        if (ta == 1 && tb == 1) v += rn[R_HQQK + i * 7 + j];
-        if (ta == 1 && tb == 2) v += rn[R_HQDK + i * 7 + j];
-        if (ta == 2 && tb == 1) v += rn[R_HQDK + j * 7 + i];
-      }
-      if (a == b) v += wdiag_const(kc, rec, a, has_next) + sg[a] + delta_w;
-      S.M[a * LDM + b] += v;
-    } else if (it < 848) {
-      const int q = it - 784, ya = q >> 3, yb = q & 7, a = yrow(ya), b = yrow(yb);
-      double v = rec[R_HYB + q];
+    if (it < 49) {
+      const int i = it / 7, j = it - 7 * i, ij = it, ji = j * 7 + i;
+      const double al[4] = {C.a_um, 1.0, C.a_dq, C.a_ddq}, be[4] = {C.b_um, 0.0, 1.0, C.b_ddq};
+      const int off[4] = {oU, oQ, oDQ, oDDQ};
+      double hqq = 0.0, hqd = 0.0, hdq = 0.0, kqq = 0.0, kqd = 0.0, kdq = 0.0;
+      if (has_next) { hqq = Hx[ij]; hqd = Hx[49 + ij]; hdq = Hx[49 + ji]; kqq = Hx[98 + ij]; kqd = Hx[147 + ij]; kdq = Hx[147 + ji]; }
+      const double own = C.a_u * C.a_u * Hk[ij] + C.a_u * C.b_u * (Hk[49 + ij] + Hk[49 + ji]);
+#pragma unroll
+      for (int ta = 0; ta < 4; ta++)
+#pragma unroll
+        for (int tb = 0; tb < 4; tb++) {
+          double v = al[ta] * al[tb] * hqq + al[ta] * be[tb] * hqd + be[ta] * al[tb] * hdq;
+          if (ta == 0 && tb == 0) v += own;
+          if (ta == 1 && tb == 1) v += kqq;
+          if (ta == 1 && tb == 2) v += kqd;
+          if (ta == 2 && tb == 1) v += kdq;
+          const int a = off[ta] + i;
+          if (ta == tb && i == j) v += wdiag_const(kc, dpd, a, has_next) + sg[a] + delta_w;
+          S.M[a * LDM + off[tb] + j] += v;
+        }
+    } else if (it < 113) {
+      const int q = it - 49, ya = q >> 3, yb = q & 7, a = yrow(ya), b = yrow(yb);
+      double v = S.Hc[q];
       if (a == b) v += sg[a] + delta_w;
       S.M[a * LDM + b] += v;
-    } else if (it < 856) {
-      const int q = it - 848, a = q == 0 ? oUPHI : (q == 7 ? oDDPHI : oVLIN + q - 1);
-      S.M[a * LDM + a] += wdiag_const(kc, rec, a, has_next) + sg[a] + delta_w;
+    } else if (it < 121) {
+      const int q = it - 113, a = q == 0 ? oUPHI : (q == 7 ? oDDPHI : oVLIN + q - 1);
+      S.M[a * LDM + a] += wdiag_const(kc, dpd, a, has_next) + sg[a] + delta_w;
     } else {
-      const int q = it - 856, wh = q / 6, m = q - 6 * wh;
-      const double v = (wh < 2 ? -2 * kc.w2 : -2 * kc.w5 * kc.idt) * rec[R_DPD + m];
+      const int q = it - 121, wh = q / 6, m = q - 6 * wh;
+      const double v = (wh < 2 ? -2 * kc.w2 : -2 * kc.w5 * kc.idt) * dpd[m];
       const int a = oVLIN + m, b = wh < 2 ? oDPHI : oDDPHI;
       if (wh & 1) S.M[b * LDM + a] += v; else S.M[a * LDM + b] += v;
     }
   }
 }
+
+// Products with the constant rows of G (the integrator): they act on whole index blocks with scalar
+// coefficients, so one item handles the three x-rows (q_j, dq_j, ddq_j) — or
+// (phi, dphi, ddphi) for j = 7 — of one vector and emits the five columns (um_j, q_j, dq_j, ddq_j, u_j).
+struct TrivOut { double um, q, dq, ddq, u; };
+BMPC_DEV TrivOut triv_combine(const Config& C, double m1, double m2, double m3) {
+  TrivOut o;
+  o.um = C.a_um * m1 + C.b_um * m2 + C.c_um * m3;
+  o.q = m1;
+  o.dq = C.a_dq * m1 + m2;
+  o.ddq = C.a_ddq * m1 + C.b_ddq * m2 + m3;
+  o.u = C.a_u * m1 + C.b_u * m2 + C.c_u * m3;
+  return o;
+}
+// x-rows (0..35) and z-columns (0..51) addressed by item index j (0..6 joints, 7 = path parameter)
+BMPC_DEV int trow(int j, int t) { return j < 7 ? 7 * t + j : 33 + t; }              // t = 0, 1, 2
+BMPC_DEV int tcol(int j, int t) { return j < 7 ? (t == 0 ? oU : (t == 1 ? oQ : (t == 2 ? oDQ : oDDQ))) + j : (t == 0 ? oUPHI : oPHI + t - 1); }   // t = 0..3
 
 // 8 x 8 Cholesky factor of Q_uu in registers; Lr holds L with the RECIPROCAL diagonal.  Every thread
 // that needs the factor computes it itself from shared memory (no broadcast, no extra barrier; the
@@ -259,53 +300,55 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 
 // One backward Riccati step for stage k.  On entry S.M = P_{k+1} (zero for k = N-1), S.pv = p_{k+1}.
 // On exit S.M = P_k, S.pv = p_k, gains stored in W.Kk / W.kap.  Returns false if Q_uu is not PD.
-// The dense block products run as 8 x 8 DMMA tiles (mma_tile); the constant rows of G are applied
-// from the tcr / tcc tables in the tile epilogues.
+// Every product with G = [A_hat | B] is split into the constant integrator rows (a cheap pass, see
+// triv_combine) and the 12 dense kinematic rows, which run as 8 x 8 DMMA tiles on top of the result of
+// the pass (mma_rowblock: A fragments shared by the tiles of a row block).
 BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
-  const double* rec = W.rec + (size_t)k * R_SIZE;
   const bool first = k == 0;      // stage 0: the previous block is fixed -> only the u-columns
-  add_W(cx, C, W, kc, S, k, delta_w);
-  PAR_FOR(i, NK * NZ) S.GK[i] = rec[R_GK + i];
-  PAR_FOR(i, NX) S.mv[i] = W.gh[NX * k + i] + S.pv[i];
-  PAR_FOR(i, NE) S.cv[i] = W.c[NE * k + i];
-  PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * rec[R_DPD + m] * kc.idt;
+  const double* GKs = S.GKb[k & 1];
+  const double* Hk = S.Hn[k & 1];
+  const int nw = ctx_nwarps(cx);
+  // ---- phase 1: M = P_{k+1} + W~_kk + delta_w I
+  add_W(cx, C, kc, S, k, delta_w);
+  PAR_FOR(i, NX) S.mv[i] = S.ghs[i] + S.pv[i];
+  PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * S.Hc[64 + m] * kc.idt;
   BMPC_SYNC();
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
-  // ---- YZ = M[:, x] G  (44 x 52): 6 x 7 tiles, inner dimension = the 12 kinematic rows
-  {
-    const int tj0 = first ? 5 : 0, ntj = 7 - tj0;
-    TILE_FOR(t, 6 * ntj) {
-      const int ti = t / ntj, tj = tj0 + t - ntj * ti;
-      mma_tile(cx, 3,
-               [&](int r, int kk) { return S.M[(8 * ti + r) * LDM + 8 + rKIN + kk]; },
-               [&](int kk, int c) { return S.GK[kk * NZ + 8 * tj + c]; },
-               [&](int r, int c, double v) {
-                 const int i = 8 * ti + r, col = 8 * tj + c;
-                 if (i < NX && col < NZ) {
-                   const double* Mr = S.M + i * LDM + 8;
+  // ---- phase 2a: integrator part of YZ = M[:, x] G (44 x 52) and t = M[:, x] c + m
+  PAR_FOR(it, NX * 8) {
+    const int i = it >> 3, j = it & 7;
+    const double* Mr = S.M + i * LDM + 8;
+    const TrivOut o = triv_combine(C, Mr[trow(j, 0)], Mr[trow(j, 1)], Mr[trow(j, 2)]);
+    double* Yr = S.YZ + i * LDY;
+    Yr[tcol(j, 0)] = o.um; Yr[tcol(j, 1)] = o.q; Yr[tcol(j, 2)] = o.dq; Yr[tcol(j, 3)] = o.ddq; Yr[NX + j] = o.u;
+    Yr[oPPOS + j] = 0.0;                      // columns p_pos, p_rot, v have no integrator rows
+    if (j < 4) Yr[oPPOS + 8 + j] = 0.0;
+  }
+  PAR_FOR(i, NX) {
+    const double* Mr = S.M + i * LDM + 8;
+    double a0 = S.mv[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                   for (int q = 0; q < 3; q++) v += S.tcc[3 * col + q] * Mr[S.tcr[3 * col + q]];
-                   S.YZ[i * LDY + col] = v;
-                 }
-               });
-    }
-    // t = M[:, x] c + m
-    PAR_FOR(i, NX) {
-      const double* Mr = S.M + i * LDM + 8;
-      double a0 = S.mv[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int l = 0; l < NE; l += 4) { a0 += Mr[l] * S.cv[l]; a1 += Mr[l + 1] * S.cv[l + 1]; a2 += Mr[l + 2] * S.cv[l + 2]; a3 += Mr[l + 3] * S.cv[l + 3]; }
-      S.tv[i] = (a0 + a1) + (a2 + a3);
-    }
+    for (int l = 0; l < NE; l += 4) { a0 += Mr[l] * S.cv[l]; a1 += Mr[l + 1] * S.cv[l + 1]; a2 += Mr[l + 2] * S.cv[l + 2]; a3 += Mr[l + 3] * S.cv[l + 3]; }
+    S.tv[i] = (a0 + a1) + (a2 + a3);
   }
   BMPC_SYNC();
-  // ---- columns u_k of Q = E^T M E + O-terms  (52 x 8): 7 tiles
+  // ---- phase 2b: YZ += M[:, kin] GK: 6 row blocks x (4 + 3) column tiles, 3 k-steps
+  for (int per = (12 + nw - 1) / nw, t = ctx_warp(cx) * per; t < 12 && t < (ctx_warp(cx) + 1) * per; t++) {
+    const int ti = t >> 1, tj0 = (t & 1) ? 4 : 0, nt = (t & 1) ? 3 : 4;
+    mma_rowblock<3, 4>(cx, nt,
+        [&](int r, int kk) { return S.M[(8 * ti + r) * LDM + 8 + rKIN + kk]; },
+        [&](int tt, int kk, int c) { return GKs[kk * NZ + 8 * (tj0 + tt) + c]; },
+        [&](int tt, int r, int c) { const int i = 8 * ti + r, col = 8 * (tj0 + tt) + c; return (i < NX && col < NZ) ? S.YZ[i * LDY + col] : 0.0; },
+        [&](int tt, int r, int c, double v) { const int i = 8 * ti + r, col = 8 * (tj0 + tt) + c; if (i < NX && col < NZ) S.YZ[i * LDY + col] = v; });
+  }
+  BMPC_SYNC();
+  // ---- phase 3: columns u_k of Q = E^T M E + O-terms  (52 x 8): 7 tiles
   {
     const int ti0 = first ? 5 : 0;
     TILE_FOR(t, 7 - ti0) {
       const int ti = ti0 + t;
       mma_tile(cx, 3,
-               [&](int r, int kk) { return S.GK[kk * NZ + 8 * ti + r]; },
+               [&](int r, int kk) { return GKs[kk * NZ + 8 * ti + r]; },
                [&](int kk, int c) { return S.YZ[(8 + rKIN + kk) * LDY + NX + c]; },
                [&](int r, int j, double v) {
                  const int a = 8 * ti + r;
@@ -313,8 +356,8 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
 #pragma unroll
                  for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + NX + j];
                  if (a < NX) {
-                   v += S.YZ[j * LDY + a] + ou_entry(rec, S.alc, S.bec, j, a);
-                   if (a >= oVLIN && a < oVLIN + 6) v += S.GK[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
+                   v += S.YZ[j * LDY + a] + ou_entry(Hk, S.alc, S.bec, j, a);
+                   if (a >= oVLIN && a < oVLIN + 6) v += GKs[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
                  } else {
                    const int i = a - NX;
                    v += S.YZ[i * LDY + NX + j] + S.YZ[j * LDY + NX + i] + S.M[i * LDM + j];
@@ -327,7 +370,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
       const int a = first ? NX + ai : ai;
       double v = 0.0;
 #pragma unroll
-      for (int r = 0; r < NK; r++) v += S.GK[r * NZ + a] * S.tv[8 + rKIN + r];
+      for (int r = 0; r < NK; r++) v += GKs[r * NZ + a] * S.tv[8 + rKIN + r];
 #pragma unroll
       for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.tv[8 + S.tcr[3 * a + q]];
       if (a >= NX) v += S.tv[a - NX];
@@ -336,15 +379,16 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     }
   }
   BMPC_SYNC();
-  // ---- gains: K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u; the factor is recomputed per thread
+  // ---- phase 4, warps 0-1: gains K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u (one column per
+  // thread, each with its own register copy of the 8 x 8 factor).  Other warps: integrator part and
+  // O-terms of Q_ss into S.M (M is dead after phase 3), then the data of stage k - 1.
   double* K = W.Kk + (size_t)k * NU * NX;
   double* kap = W.kap + k * NU;
-  bool ok;
-  {
+  if (in_role(cx, 0, 2)) {
     double L[NU][NU];
-    ok = chol8(S.Qu, L);
-    if (ok) {
-      PAR_FOR(col, (first ? 0 : NX) + 1) {
+    if (!chol8(S.Qu, L)) S.flag[3] = 1;
+    else {
+      ROLE_FOR(col, (first ? 0 : NX) + 1, 0, 2) {
         const bool isk = col == (first ? 0 : NX);
         double bcol[NU];
 #pragma unroll
@@ -371,34 +415,52 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
       }
     }
   }
-  if (!ok) return false;
-  BMPC_SYNC();
-  if (first) return true;
-  // ---- P_k = Q_ss + Q_su K  (symmetric; upper tiles, mirrored), p_k = q_s + Q_su kappa
-  TILE_FOR(t, 21) {
-    int ti = 0, rem = t;
-    while (rem >= 6 - ti) { rem -= 6 - ti; ti++; }
-    const int tj = ti + rem;
-    mma_tile(cx, 5,
-             [&](int r, int kk) { return kk < NK ? S.GK[kk * NZ + 8 * ti + r] : S.Qu[(8 * ti + r) * LDQ + kk - NK]; },
-             [&](int kk, int c) { return kk < NK ? S.YZ[(8 + rKIN + kk) * LDY + 8 * tj + c] : S.Ks[(kk - NK) * NX + 8 * tj + c]; },
-             [&](int r, int c, double v) {
-               const int a = 8 * ti + r, b = 8 * tj + c;
-               if (a >= NX || b >= NX || a > b) return;
+  if (!first) {
+    // Q_ss, integrator rows of G^T Y: item (j, b) -> rows um_j, q_j, dq_j, ddq_j of column b; O-terms:
+    // rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv (E^T O [I 0] + transpose)
+    ROLE_FOR(it, 8 * NX, 2, nw) {
+      const int j = it / NX, b = it - NX * j;
+      const TrivOut o = triv_combine(C, S.YZ[(8 + trow(j, 0)) * LDY + b], S.YZ[(8 + trow(j, 1)) * LDY + b], S.YZ[(8 + trow(j, 2)) * LDY + b]);
+      double vv[4] = {o.um, o.q, o.dq, o.ddq};
 #pragma unroll
-               for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + b];
-               // E^T O [I 0] + transpose: rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv
-               if (b >= oVLIN && b < oVLIN + 6) {
-                 const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : 0.0);
-                 v += S.GK[(6 + b - oVLIN) * NZ + a] * ovv + g35 * S.odv[b - oVLIN];
-               }
-               if (a >= oVLIN && a < oVLIN + 6) {
-                 const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : 0.0);
-                 v += S.GK[(6 + a - oVLIN) * NZ + b] * ovv + g35 * S.odv[a - oVLIN];
-               }
-               S.M[a * LDM + b] = v;
-               S.M[b * LDM + a] = v;
-             });
+      for (int t = 0; t < 4; t++) {
+        const int a = tcol(j, t);
+        double v = vv[t];
+        if (b >= oVLIN && b < oVLIN + 6) {
+          const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : 0.0);
+          v += GKs[(6 + b - oVLIN) * NZ + a] * ovv + g35 * S.odv[b - oVLIN];
+        }
+        S.M[a * LDM + b] = v;
+      }
+    }
+    ROLE_FOR(it, 12 * NX, 2, nw) {           // rows p_pos, p_rot, v: no integrator part
+      const int a = oPPOS + it / NX, b = it - NX * (it / NX);
+      double v = 0.0;
+      if (b >= oVLIN && b < oVLIN + 6) v += GKs[(6 + b - oVLIN) * NZ + a] * ovv;
+      if (a >= oVLIN && a < oVLIN + 6) {
+        const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : 0.0);
+        v += GKs[(6 + a - oVLIN) * NZ + b] * ovv + g35 * S.odv[a - oVLIN];
+      }
+      S.M[a * LDM + b] = v;
+    }
+    if (in_role(cx, 2, nw)) stage_prefetch(cx, C, W, S, k - 1, 2, nw);
+  }
+  BMPC_SYNC();
+  if (S.flag[3]) { BMPC_SYNC(); return false; }   // (barrier: nobody re-arms the flag before everyone has read it)
+  if (first) return true;
+  // ---- phase 5: P_k = Q_ss + Q_su K (symmetric: upper tiles, mirrored), p_k = q_s + Q_su kappa
+  for (int ti = ctx_warp(cx); ti < 6; ti = nw == 4 ? ((ti == 2 || ti == 3) ? 7 - ti : 6) : ti + nw) {   // 4 warps: 6, 5, 4 + 1, 3 + 2 tiles
+    const int nt = 6 - ti;
+    mma_rowblock<5, 6>(cx, nt,
+        [&](int r, int kk) { return kk < NK ? GKs[kk * NZ + 8 * ti + r] : S.Qu[(8 * ti + r) * LDQ + kk - NK]; },
+        [&](int tt, int kk, int c) { return kk < NK ? S.YZ[(8 + rKIN + kk) * LDY + 8 * (ti + tt) + c] : S.Ks[(kk - NK) * NX + 8 * (ti + tt) + c]; },
+        [&](int tt, int r, int c) { const int a = 8 * ti + r, b = 8 * (ti + tt) + c; return (a < NX && b < NX) ? S.M[a * LDM + b] : 0.0; },
+        [&](int tt, int r, int c, double v) {
+          const int a = 8 * ti + r, b = 8 * (ti + tt) + c;
+          if (a >= NX || b >= NX || a > b) return;
+          S.M[a * LDM + b] = v;
+          S.M[b * LDM + a] = v;
+        });
   }
   PAR_FOR(a, NX) {
     double v = S.qv[a];
@@ -470,7 +532,7 @@ BMPC_DEV void adjoint_rhs(const Ctx& cx, const Config& C, const Work& W, const K
     const double* dw = W.dx + NX * k;
     const double* dwp = dw - NX;
     const double* dwn = dw + NX;
-    double a = W.gh[NX * k + r] + (delta_w + W.sig[NX * k + r] + wdiag_const(kc, rec, r, has_next)) * dw[r];
+    double a = W.gh[NX * k + r] + (delta_w + W.sig[NX * k + r] + wdiag_const(kc, rec + R_DPD, r, has_next)) * dw[r];
     const int ya = yidx(r);
     if (ya >= 0) {
 #pragma unroll
@@ -527,10 +589,12 @@ BMPC_DEV void adjoint_sweep(const Ctx& cx, const Config& C, const Work& W, Smem&
 
 // Backward + forward + adjoint sweeps: dx (primal step) and ynew (equality multipliers of the full
 // step).  kkt_prepare must have run for the current iterate.
-BMPC_DEV bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
+BMPC_NOINLINE bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
   const KktCoef kc = kkt_coef(C, p);
   PAR_FOR(i, NX * NX) S.M[i] = 0.0;
   PAR_FOR(i, NX) S.pv[i] = 0.0;
+  if (cx.tid == 0) S.flag[3] = 0;
+  stage_prefetch(cx, C, W, S, C.N - 1, 0, ctx_nwarps(cx));
   BMPC_SYNC();
   for (int k = C.N - 1; k >= 0; k--)
     if (!riccati_stage(cx, C, W, kc, S, k, delta_w)) return false;

@@ -20,7 +20,7 @@ funcs = {}
 for f in os.listdir(root):
     starts = []
     for i, l in enumerate(open(os.path.join(root, f)), 1):
-        m = re.match(r'^(?:template.*\n)?(?:BMPC_DEV|BMPC_HD|__global__|static|inline)\b.*?(\w+)\s*\(', l)
+        m = re.match(r'^(?:template.*\n)?(?:BMPC_DEV|BMPC_HD|BMPC_NOINLINE|__global__|static|inline)\b.*?(\w+)\s*\(', l)
         if m and not l.startswith(' '): starts.append((i, m.group(1)))
     funcs[f] = starts
 def fn(file, line):
@@ -31,12 +31,15 @@ def fn(file, line):
 rows = list(csv.reader(open(srccsv)))
 hdr = rows[1]; data = rows[2:]
 iS = hdr.index('# Samples'); iB = hdr.index('stall_barrier'); iI = hdr.index('Instructions Executed')
+ST = ['stall_no_inst', 'stall_long_sb', 'stall_wait', 'stall_short_sb', 'stall_branch_resolving', 'stall_selected']
+iST = [hdr.index(x) for x in ST]
 assert len(data) == len(lines), (len(data), len(lines))
-agg = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0, 0]
+agg = collections.defaultdict(lambda: [0, 0, 0] + [0] * len(ST)); tot = [0, 0, 0]
 for r, l in zip(data, lines):
     k = fn(*l) if l else 'none'
     a = agg[k]; s, b, i = int(r[iS]), int(r[iB]), int(r[iI])
     a[0] += s; a[1] += b; a[2] += i; tot[0] += s; tot[1] += b; tot[2] += i
+    for q, ix in enumerate(iST): a[3 + q] += int(r[ix])
 print('total samples %d barrier %d inst %d' % tuple(tot))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    print(f"{k:45s} samples {v[0]:7d} ({100*v[0]/tot[0]:5.1f}%) barrier {v[1]:7d} inst {v[2]:9d} ({100*v[2]/tot[2]:5.1f}%)")
+    print(f"{k:40s} smp {100*v[0]/tot[0]:5.1f}% inst {100*v[2]/tot[2]:5.1f}% | bar {100*v[1]/max(1,v[0]):3.0f} " + " ".join(f"{n[6:10]} {100*v[3+q]/max(1,v[0]):3.0f}" for q, n in enumerate(ST)))
