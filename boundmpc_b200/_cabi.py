@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libboundmpc_b200.so")
+LIB_PATH = os.environ.get("BMPC_LIB") or os.path.join(_HERE, "libboundmpc_b200.so")   # BMPC_LIB: development builds
 _lib = None
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -20,7 +20,17 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+TIMING_LIB = os.path.join(HERE, "libboundmpc_b200_timing.so")   # development build with per-phase cycle counters
+
+
+def build(force=False, verbose=False, timing=False):
+    if timing:
+        nvcc = os.environ.get("NVCC", "nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + ["-DBMPC_TIMING", "-o", TIMING_LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        return TIMING_LIB
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -34,4 +44,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, timing="--timing" in sys.argv))

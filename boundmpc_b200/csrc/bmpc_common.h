@@ -28,6 +28,15 @@
 #define BMPC_LDG(ptr) __ldg(ptr)
 #endif
 
+// optional per-phase cycle accounting of thread 0 (development build, -DBMPC_TIMING)
+#ifdef BMPC_TIMING
+#define BMPC_TMARK(id) do { if (cx.tid == 0) { long long t_ = clock64(); cx.tm[id] += t_ - cx.tm[63]; cx.tm[63] = t_; } } while (0)
+#define BMPC_TMARK2(id) do { if (cx.tid == 64) { long long t_ = clock64(); cx.tm[id] += t_ - cx.tm[62]; cx.tm[62] = t_; } } while (0)
+#else
+#define BMPC_TMARK(id) ((void)0)
+#define BMPC_TMARK2(id) ((void)0)
+#endif
+
 #define PAR_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nt)
 // items of a phase executed by a single warp (no CTA barrier needed between such phases)
 #ifdef BMPC_HOST_EMU
@@ -47,6 +56,9 @@ namespace bmpc {
 struct Ctx {
   int tid, nt;
   double* red;  // shared scratch for block reductions (8 values x 8 warps)
+#ifdef BMPC_TIMING
+  long long* tm;  // [64] per-phase cycles, [63] = last time stamp
+#endif
 };
 BMPC_DEV int ctx_warp(const Ctx& cx) { return cx.tid >> 5; }
 BMPC_DEV int ctx_nwarps(const Ctx& cx) { return (cx.nt + 31) >> 5; }
@@ -105,21 +117,72 @@ BMPC_DEV void mma_rowblock(const Ctx& cx, int nt, FA a, FB b, FC cin, FE epi) {
       }
 #else
   const int lane = cx.tid & 31, r = lane >> 2, q = lane & 3;
-  double av[KS];
+  // k-step outer, tile inner: the NT accumulator pairs are independent, so the (long-latency) DMMAs of
+  // one k-step are all in flight together instead of forming one serial chain per tile
+  double av[KS], acc[NT][2];
 #pragma unroll
   for (int ks = 0; ks < KS; ks++) av[ks] = a(r, 4 * ks + q);
 #pragma unroll
   for (int t = 0; t < NT; t++) {
-    if (t < nt) {
-      double c0 = cin(t, r, 2 * q), c1 = cin(t, r, 2 * q + 1);
+    acc[t][0] = t < nt ? cin(t, r, 2 * q) : 0.0;
+    acc[t][1] = t < nt ? cin(t, r, 2 * q + 1) : 0.0;
+  }
 #pragma unroll
-      for (int ks = 0; ks < KS; ks++) {
+  for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      if (t < nt) {
         const double bv = b(t, 4 * ks + q, r);
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(av[ks]), "d"(bv));
+                     : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(av[ks]), "d"(bv));
       }
-      epi(t, r, 2 * q, c0);
-      epi(t, r, 2 * q + 1, c1);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t < nt) {
+      epi(t, r, 2 * q, acc[t][0]);
+      epi(t, r, 2 * q + 1, acc[t][1]);
+    }
+  }
+#endif
+}
+// Column block of tiles that share their B fragments: C_t(r, c) = sum_{kk < 4 KS} a(t, r, kk) * b(kk, c) for
+// t < nt (<= NT); same interleaving of the independent accumulators as mma_rowblock.
+template <int KS, int NT, class FA, class FB, class FE>
+BMPC_DEV void mma_colblock(const Ctx& cx, int nt, FA a, FB b, FE epi) {
+#ifdef BMPC_HOST_EMU
+  (void)cx;
+  for (int t = 0; t < nt; t++)
+    for (int r = 0; r < 8; r++)
+      for (int c = 0; c < 8; c++) {
+        double v = 0.0;
+        for (int kk = 0; kk < 4 * KS; kk++) v += a(t, r, kk) * b(kk, c);
+        epi(t, r, c, v);
+      }
+#else
+  const int lane = cx.tid & 31, r = lane >> 2, q = lane & 3;
+  double bv[KS], acc[NT][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) bv[ks] = b(4 * ks + q, r);
+#pragma unroll
+  for (int t = 0; t < NT; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      if (t < nt) {
+        const double av = a(t, r, 4 * ks + q);
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(av), "d"(bv[ks]));
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t < nt) {
+      epi(t, r, 2 * q, acc[t][0]);
+      epi(t, r, 2 * q + 1, acc[t][1]);
     }
   }
 #endif
@@ -222,6 +285,22 @@ enum {
   F_DQ = F_CS + 7,         // [7]
   F_SIZE = F_DQ + 7
 };
+
+// asynchronous 8-byte copy global -> shared (LDGSTS): issued back to back, completed by cp_async_wait()
+// of the issuing thread plus a barrier for the readers
+BMPC_DEV void cp_async8(double* dst_smem, const double* src) {
+#ifdef BMPC_HOST_EMU
+  *dst_smem = *src;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#endif
+}
+BMPC_DEV void cp_async_wait() {
+#ifndef BMPC_HOST_EMU
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 
 // one copy each of the transcendental routines
 BMPC_NOINLINE double bmpc_log(double v) { return log(v); }

@@ -65,6 +65,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
   }
   if (cx.tid == 0) S.flag[1] = 0;   // filter size
   BMPC_SYNC();
+  BMPC_TMARK(22);
 
   int nbnd = 0;
   for (int i = 0; i < NX; i++) nbnd += (C.lb[i] > -1e300) + (C.ub[i] < 1e300);
@@ -105,6 +106,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       const int ops[8] = {RED_MAX, RED_MAX, RED_SUM, RED_SUM, RED_MIN, RED_MAX, RED_SUM, RED_SUM};
       block_reduce<8>(cx, rv, ops);
     }
+    BMPC_TMARK(6);
     const double dinf = rv[0], pinf = rv[1], ysum = rv[2], zsum = rv[3], szmin = rv[4], szmax = rv[5], th_cur = rv[6];
     fval = rv[7];
     const double sd = fmax(C.s_max, (ysum + zsum) / (ne + nzcnt)) / C.s_max;
@@ -127,6 +129,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
     // ---- search direction with inertia correction
     double dwreg = 0.0;
     kkt_prepare(cx, C, W, mu);
+    BMPC_TMARK(17);
     bool ok = kkt_solve(cx, C, W, p, S, 0.0);
     if (!ok) {
       dwreg = delta_w_last == 0.0 ? 1e-4 : fmax(1e-20, delta_w_last / 3);
@@ -184,6 +187,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       const int ops[4] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM};
       block_reduce<4>(cx, sv4, ops);
     }
+    BMPC_TMARK(18);
     const double apr = sv4[0], adu = sv4[1], dphi = sv4[2], phi_cur = fval + sv4[3];
     // ---- filter line search (Waechter & Biegler 2006, Alg. A, without restoration phase / SOC)
     double alpha = apr;
@@ -193,6 +197,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
       PAR_FOR(i, n) W.xt[i] = W.x[i] + alpha * W.dx[i];
       PAR_FOR(i, nd) W.st[i] = W.s[i] + alpha * W.ds[i];
       BMPC_SYNC();
+      BMPC_TMARK(19);
       eval_values(cx, C, W, p, W.xt, W.ct, W.dtr);
       double tv2[2] = {0.0, 0.0};   // theta_trial, phi_trial
       PAR_FOR(i, ne) tv2[0] += fabs(W.ct[i]);
@@ -208,6 +213,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
         const int ops[2] = {RED_SUM, RED_SUM};
         block_reduce<2>(cx, tv2, ops);
       }
+      BMPC_TMARK(20);
       const double th_t = tv2[0], ph_t = tv2[1];
       if (!(th_t == th_t) || !(ph_t == ph_t) || !(th_t < 1e300) || !(fabs(ph_t) < 1e300) || th_t > theta_max) continue;
       bool filt_ok = true;
@@ -255,6 +261,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
     }
     PAR_FOR(i, ne) W.y[i] += alpha * (W.ynew[i] - W.y[i]);
     BMPC_SYNC();
+    BMPC_TMARK(21);
   }
 
   // ---- report in the reference's conventions: x, g, lam_g, lam_x (CasADi: L = f + lam_g.g + lam_x.x)
@@ -283,6 +290,7 @@ BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem
   }
   if (cx.tid == 0) { *io.f = fval; *io.kkt = kkt_final; *io.iters = it; *io.status = status; }
   BMPC_SYNC();
+  BMPC_TMARK(23);
 }
 
 }  // namespace bmpc

@@ -28,15 +28,31 @@ struct BatchIO {
   int32_t *iters, *status;
 };
 
+#ifdef BMPC_TIMING
+__device__ unsigned long long g_phase_cycles[64];
+extern "C" int bmpc_phase_cycles(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+  if (e == cudaSuccess && reset) { unsigned long long z[64] = {0}; e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C, int batch, BatchIO io, double* ws,
                                                          size_t ws_stride, unsigned int* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+#ifdef BMPC_TIMING
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red, S.tm};
+  if (threadIdx.x < 64) S.tm[threadIdx.x] = threadIdx.x >= 62 ? clock64() : 0;
+  __syncthreads();
+#else
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
+#endif
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
   build_tables(cx, C, S);
+  phase_kin_jacobian_init(cx, C, W);
   for (;;) {
     if (threadIdx.x == 0) S.flag[2] = (int)atomicAdd(counter, 1u);
     __syncthreads();
@@ -47,13 +63,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
                   io.lam_g + (size_t)b * C.m, io.lam_x + (size_t)b * C.n, io.f + b, io.kkt + b, io.iters + b, io.status + b};
     solve_instance(cx, C, W, S, ii);
   }
+#ifdef BMPC_TIMING
+  if (threadIdx.x < 62) atomicAdd(&g_phase_cycles[threadIdx.x], (unsigned long long)S.tm[threadIdx.x]);
+#endif
 }
 
 // launch variants: (threads per CTA, resident CTAs per SM the register budget is compiled for)
 typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, unsigned int*);
 struct SolveVariant { int threads, minb; solve_fn fn; };
 static const SolveVariant kVariants[] = {
+#ifdef BMPC_TIMING
+    {128, 3, k_solve<128, 3>},
+#else
     {128, 3, k_solve<128, 3>}, {192, 2, k_solve<192, 2>}, {256, 1, k_solve<256, 1>}, {256, 2, k_solve<256, 2>},
+#endif
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -66,10 +89,15 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant
                                                            size_t ws_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+#ifdef BMPC_TIMING
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red, S.tm};
+#else
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
+#endif
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
   build_tables(cx, C, S);
+  phase_kin_jacobian_init(cx, C, W);
   const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
     EvalIO e{io.x + b * n, io.p + (size_t)b * C.np, io.lam ? io.lam + b * nl : nullptr, io.f ? io.f + b : nullptr,

@@ -494,8 +494,10 @@ BMPC_DEV void phase_kin_hessian(const Ctx& cx, const Config& C, const Work& W) {
 
 // Phase 5: kinematic rows of [A_hat | B] (first derivatives).  One item per (stage, joint).
 //   d pos / dq_i = z_i x r_i ;  d(Jv dq)/dq_i = z_i x W_i + Om_{<i} x (z_i x r_i) ;  d(Jw dq)/dq_i = z_i x Om_{>i}
+// Structural zeros and the identity of the p_rot columns of GK: the sparsity pattern never changes, so this
+// runs once per CTA workspace (kernel start), not per evaluation.
 BMPC_DEV void phase_kin_jacobian_init(const Ctx& cx, const Config& C, const Work& W) {
-  ROLE_FOR(it, C.N * NZ, 2, ctx_nwarps(cx)) {   // zero fill + identity of the p_rot columns
+  PAR_FOR(it, C.N * NZ) {
     const int k = it / NZ, col = it - NZ * k;
     double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
     for (int r = 0; r < NK; r++) GK[r * NZ + col] = 0.0;
@@ -569,26 +571,36 @@ BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const 
 BMPC_NOINLINE void eval_values(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* c, double* d) {
   phase_integrate(cx, C, W, x, c);
   BMPC_SYNC();
+  BMPC_TMARK(3);
   phase_fk(cx, C, W);
   phase_path(cx, C, W, p, x, d, nullptr, 0, 1);
   BMPC_SYNC();
+  BMPC_TMARK(4);
   phase_kin_residual(cx, C, W, x, c);
   BMPC_SYNC();
+  BMPC_TMARK(5);
 }
 
 BMPC_NOINLINE void eval_full(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x) {
   phase_integrate(cx, C, W, x, W.c);
   BMPC_SYNC();
+  BMPC_TMARK(0);
   phase_fk(cx, C, W);
   phase_path(cx, C, W, p, x, W.d, nullptr, 1, 1);
-  phase_kin_jacobian_init(cx, C, W);
   BMPC_SYNC();
+  BMPC_TMARK(1);
   phase_kin_residual(cx, C, W, x, W.c);
+  BMPC_TMARK(32);
   phase_kin_hessian(cx, C, W);
+  BMPC_TMARK(33);
   phase_kin_jacobian(cx, C, W);
+  BMPC_TMARK(34);
   phase_path_blocks(cx, C, W, p);
+  BMPC_TMARK(35);
   phase_grad_f(cx, C, W, p, x, W.gradf);
+  BMPC_TMARK(36);
   BMPC_SYNC();
+  BMPC_TMARK(2);
 }
 
 // trivial (non-kinematic) rows of G = [A_hat | B]: for a column of z = (s_k, u_k) the up-to-three

@@ -31,6 +31,7 @@ struct Smem {
   double Hn[2][4 * 49 + 4];    // HQQN, HQDN, HQQK, HQDK of stage k in buffer k & 1
   double Hc[64 + 8 + NX];      // current stage only: HYB [64], DPD [6], sig [44]
   double ghs[NX];              // g^_k
+  double Muu[64];              // copy of M[0..7][0..7] (needed by Q_uu after S.M has been reused for Q_ss)
   double YZ[NX * LDY];         // M[:, x] G  (rows 0..7 = u rows "Z", rows 8..43 = x rows "Y")
   double Qu[56 * LDQ];         // columns u_k of Q: rows 0..43 = Q_su, rows 44..51 = Q_uu
   double Ks[NU * NX + 4];      // feedback gain K_k
@@ -47,6 +48,9 @@ struct Smem {
   double red[8 * 8];           // block reductions (8 values x up to 8 warps)
   double filt[2 * 64];         // filter entries (theta, phi)
   int flag[4];
+#ifdef BMPC_TIMING
+  long long tm[64];
+#endif
 };
 
 // table form of triv_col, built once per kernel
@@ -195,12 +199,12 @@ BMPC_DEV void stage_prefetch(const Ctx& cx, const Config& C, const Work& W, Smem
   const double* rec = W.rec + (size_t)k * R_SIZE;
   double* GK = S.GKb[k & 1];
   double* Hk = S.Hn[k & 1];
-  ROLE_FOR(i, NK * NZ, w0, w1) GK[i] = rec[R_GK + i];
-  ROLE_FOR(i, 4 * 49, w0, w1) Hk[i] = rec[R_HQQN + i];
-  ROLE_FOR(i, 64, w0, w1) S.Hc[i] = rec[R_HYB + i];
-  ROLE_FOR(i, 6, w0, w1) S.Hc[64 + i] = rec[R_DPD + i];
-  ROLE_FOR(i, NX, w0, w1) { S.Hc[72 + i] = W.sig[NX * k + i]; S.ghs[i] = W.gh[NX * k + i]; }
-  ROLE_FOR(i, NE, w0, w1) S.cv[i] = W.c[NE * k + i];
+  ROLE_FOR(i, NK * NZ, w0, w1) cp_async8(GK + i, rec + R_GK + i);
+  ROLE_FOR(i, 4 * 49, w0, w1) cp_async8(Hk + i, rec + R_HQQN + i);
+  ROLE_FOR(i, 64, w0, w1) cp_async8(S.Hc + i, rec + R_HYB + i);
+  ROLE_FOR(i, 6, w0, w1) cp_async8(S.Hc + 64 + i, rec + R_DPD + i);
+  ROLE_FOR(i, NX, w0, w1) { cp_async8(S.Hc + 72 + i, W.sig + NX * k + i); cp_async8(S.ghs + i, W.gh + NX * k + i); }
+  ROLE_FOR(i, NE, w0, w1) cp_async8(S.cv + i, W.c + NE * k + i);
 }
 
 // S.M += W~_kk + delta_w I, added block by block from the staged stage records (the 44 x 44 block is
@@ -313,6 +317,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
   PAR_FOR(i, NX) S.mv[i] = S.ghs[i] + S.pv[i];
   PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * S.Hc[64 + m] * kc.idt;
   BMPC_SYNC();
+  BMPC_TMARK(8);
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
   // ---- phase 2a: integrator part of YZ = M[:, x] G (44 x 52) and t = M[:, x] c + m
   PAR_FOR(it, NX * 8) {
@@ -324,6 +329,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     Yr[oPPOS + j] = 0.0;                      // columns p_pos, p_rot, v have no integrator rows
     if (j < 4) Yr[oPPOS + 8 + j] = 0.0;
   }
+  PAR_FOR(i, 64) S.Muu[i] = S.M[(i >> 3) * LDM + (i & 7)];
   PAR_FOR(i, NX) {
     const double* Mr = S.M + i * LDM + 8;
     double a0 = S.mv[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -332,6 +338,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     S.tv[i] = (a0 + a1) + (a2 + a3);
   }
   BMPC_SYNC();
+  BMPC_TMARK(9);
   // ---- phase 2b: YZ += M[:, kin] GK: 6 row blocks x (4 + 3) column tiles, 3 k-steps
   for (int per = (12 + nw - 1) / nw, t = ctx_warp(cx) * per; t < 12 && t < (ctx_warp(cx) + 1) * per; t++) {
     const int ti = t >> 1, tj0 = (t & 1) ? 4 : 0, nt = (t & 1) ? 3 : 4;
@@ -342,29 +349,29 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
         [&](int tt, int r, int c, double v) { const int i = 8 * ti + r, col = 8 * (tj0 + tt) + c; if (i < NX && col < NZ) S.YZ[i * LDY + col] = v; });
   }
   BMPC_SYNC();
+  BMPC_TMARK(10);
   // ---- phase 3: columns u_k of Q = E^T M E + O-terms  (52 x 8): 7 tiles
   {
+    // row tiles ti0.., dealt round-robin; the (up to two) tiles of a warp run interleaved
     const int ti0 = first ? 5 : 0;
-    TILE_FOR(t, 7 - ti0) {
-      const int ti = ti0 + t;
-      mma_tile(cx, 3,
-               [&](int r, int kk) { return GKs[kk * NZ + 8 * ti + r]; },
-               [&](int kk, int c) { return S.YZ[(8 + rKIN + kk) * LDY + NX + c]; },
-               [&](int r, int j, double v) {
-                 const int a = 8 * ti + r;
-                 if (a >= NZ || (first && a < NX)) return;
+    for (int wti = ti0 + ctx_warp(cx); wti < 7; wti += 2 * nw)
+    mma_colblock<3, 2>(cx, wti + nw < 7 ? 2 : 1,
+        [&](int tt, int r, int kk) { return GKs[kk * NZ + 8 * (wti + tt * nw) + r]; },
+        [&](int kk, int c) { return S.YZ[(8 + rKIN + kk) * LDY + NX + c]; },
+        [&](int tt, int r, int j, double v) {
+          const int a = 8 * (wti + tt * nw) + r;
+          if (a >= NZ || (first && a < NX)) return;
 #pragma unroll
-                 for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + NX + j];
-                 if (a < NX) {
-                   v += S.YZ[j * LDY + a] + ou_entry(Hk, S.alc, S.bec, j, a);
-                   if (a >= oVLIN && a < oVLIN + 6) v += GKs[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
-                 } else {
-                   const int i = a - NX;
-                   v += S.YZ[i * LDY + NX + j] + S.YZ[j * LDY + NX + i] + S.M[i * LDM + j];
-                 }
-                 S.Qu[a * LDQ + j] = v;
-               });
-    }
+          for (int q = 0; q < 3; q++) v += S.tcc[3 * a + q] * S.YZ[(8 + S.tcr[3 * a + q]) * LDY + NX + j];
+          if (a < NX) {
+            v += S.YZ[j * LDY + a] + ou_entry(Hk, S.alc, S.bec, j, a);
+            if (a >= oVLIN && a < oVLIN + 6) v += GKs[(6 + a - oVLIN) * NZ + NX + j] * ovv + (j == 7 ? C.c_u * S.odv[a - oVLIN] : 0.0);
+          } else {
+            const int i = a - NX;
+            v += S.YZ[i * LDY + NX + j] + S.YZ[j * LDY + NX + i] + S.Muu[i * 8 + j];
+          }
+          S.Qu[a * LDQ + j] = v;
+        });
     // q = G^T t + U^T t_u + [O_x^T c ; 0]
     PAR_FOR(ai, first ? NU : NZ) {
       const int a = first ? NX + ai : ai;
@@ -378,15 +385,46 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
       S.qv[a] = v;
     }
   }
+  if (!first) {   // (S.M is dead: phase 3 reads Q_uu's M block from S.Muu)
+  // Q_ss, integrator rows of G^T Y: item (j, b) -> rows um_j, q_j, dq_j, ddq_j of column b; O-terms:
+  // rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv (E^T O [I 0] + transpose)
+  PAR_FOR(it, 8 * NX) {
+    const int j = it / NX, b = it - NX * j;
+    const TrivOut o = triv_combine(C, S.YZ[(8 + trow(j, 0)) * LDY + b], S.YZ[(8 + trow(j, 1)) * LDY + b], S.YZ[(8 + trow(j, 2)) * LDY + b]);
+    double vv[4] = {o.um, o.q, o.dq, o.ddq};
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int a = tcol(j, t);
+      double v = vv[t];
+      if (b >= oVLIN && b < oVLIN + 6) {
+        const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : 0.0);
+        v += GKs[(6 + b - oVLIN) * NZ + a] * ovv + g35 * S.odv[b - oVLIN];
+      }
+      S.M[a * LDM + b] = v;
+    }
+  }
+  PAR_FOR(it, 12 * NX) {           // rows p_pos, p_rot, v: no integrator part
+    const int a = oPPOS + it / NX, b = it - NX * (it / NX);
+    double v = 0.0;
+    if (b >= oVLIN && b < oVLIN + 6) v += GKs[(6 + b - oVLIN) * NZ + a] * ovv;
+    if (a >= oVLIN && a < oVLIN + 6) {
+      const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : 0.0);
+      v += GKs[(6 + a - oVLIN) * NZ + b] * ovv + g35 * S.odv[a - oVLIN];
+    }
+    S.M[a * LDM + b] = v;
+  }
+  }
   BMPC_SYNC();
+  BMPC_TMARK(11);
   // ---- phase 4, warps 0-1: gains K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u (one column per
-  // thread, each with its own register copy of the 8 x 8 factor).  Other warps: integrator part and
-  // O-terms of Q_ss into S.M (M is dead after phase 3), then the data of stage k - 1.
+  // thread, each with its own register copy of the 8 x 8 factor).  Other warps: stage the data of stage k - 1.
   double* K = W.Kk + (size_t)k * NU * NX;
   double* kap = W.kap + k * NU;
   if (in_role(cx, 0, 2)) {
     double L[NU][NU];
-    if (!chol8(S.Qu, L)) S.flag[3] = 1;
+    const bool okc = chol8(S.Qu, L);
+    BMPC_TMARK(41);
+    if (!okc) S.flag[3] = 1;
     else {
       ROLE_FOR(col, (first ? 0 : NX) + 1, 0, 2) {
         const bool isk = col == (first ? 0 : NX);
@@ -415,39 +453,20 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
       }
     }
   }
+  BMPC_TMARK(42);
+  BMPC_TMARK2(48);
   if (!first) {
-    // Q_ss, integrator rows of G^T Y: item (j, b) -> rows um_j, q_j, dq_j, ddq_j of column b; O-terms:
-    // rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv (E^T O [I 0] + transpose)
-    ROLE_FOR(it, 8 * NX, 2, nw) {
-      const int j = it / NX, b = it - NX * j;
-      const TrivOut o = triv_combine(C, S.YZ[(8 + trow(j, 0)) * LDY + b], S.YZ[(8 + trow(j, 1)) * LDY + b], S.YZ[(8 + trow(j, 2)) * LDY + b]);
-      double vv[4] = {o.um, o.q, o.dq, o.ddq};
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int a = tcol(j, t);
-        double v = vv[t];
-        if (b >= oVLIN && b < oVLIN + 6) {
-          const double g35 = a == oUPHI ? C.c_um : (a == oDDPHI ? 1.0 : 0.0);
-          v += GKs[(6 + b - oVLIN) * NZ + a] * ovv + g35 * S.odv[b - oVLIN];
-        }
-        S.M[a * LDM + b] = v;
-      }
-    }
-    ROLE_FOR(it, 12 * NX, 2, nw) {           // rows p_pos, p_rot, v: no integrator part
-      const int a = oPPOS + it / NX, b = it - NX * (it / NX);
-      double v = 0.0;
-      if (b >= oVLIN && b < oVLIN + 6) v += GKs[(6 + b - oVLIN) * NZ + a] * ovv;
-      if (a >= oVLIN && a < oVLIN + 6) {
-        const double g35 = b == oUPHI ? C.c_um : (b == oDDPHI ? 1.0 : 0.0);
-        v += GKs[(6 + a - oVLIN) * NZ + b] * ovv + g35 * S.odv[a - oVLIN];
-      }
-      S.M[a * LDM + b] = v;
-    }
-    if (in_role(cx, 2, nw)) stage_prefetch(cx, C, W, S, k - 1, 2, nw);
+    if (in_role(cx, 2, nw)) stage_prefetch(cx, C, W, S, k - 1, 2, nw);   // asynchronous, completed below
+    BMPC_TMARK2(49);
+    cp_async_wait();
+    BMPC_TMARK2(52);
   }
   BMPC_SYNC();
+  BMPC_TMARK(12);
+  BMPC_TMARK2(44);
   if (S.flag[3]) { BMPC_SYNC(); return false; }   // (barrier: nobody re-arms the flag before everyone has read it)
   if (first) return true;
+  BMPC_TMARK(40);
   // ---- phase 5: P_k = Q_ss + Q_su K (symmetric: upper tiles, mirrored), p_k = q_s + Q_su kappa
   for (int ti = ctx_warp(cx); ti < 6; ti = nw == 4 ? ((ti == 2 || ti == 3) ? 7 - ti : 6) : ti + nw) {   // 4 warps: 6, 5, 4 + 1, 3 + 2 tiles
     const int nt = 6 - ti;
@@ -462,13 +481,19 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
           S.M[b * LDM + a] = v;
         });
   }
+  BMPC_TMARK(30);
+  BMPC_TMARK2(45);
   PAR_FOR(a, NX) {
     double v = S.qv[a];
 #pragma unroll
     for (int i = 0; i < NU; i++) v += S.Qu[a * LDQ + i] * S.kapv[i];
     S.pv[a] = v;
   }
+  BMPC_TMARK(31);
+  BMPC_TMARK2(46);
   BMPC_SYNC();
+  BMPC_TMARK(13);
+  BMPC_TMARK2(47);
   return true;
 }
 
@@ -595,15 +620,20 @@ BMPC_NOINLINE bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, cons
   PAR_FOR(i, NX) S.pv[i] = 0.0;
   if (cx.tid == 0) S.flag[3] = 0;
   stage_prefetch(cx, C, W, S, C.N - 1, 0, ctx_nwarps(cx));
+  cp_async_wait();
   BMPC_SYNC();
+  BMPC_TMARK(7);
   for (int k = C.N - 1; k >= 0; k--)
     if (!riccati_stage(cx, C, W, kc, S, k, delta_w)) return false;
   if (ctx_warp(cx) == 0) forward_sweep(cx, C, W, S);
   BMPC_SYNC();
+  BMPC_TMARK(14);
   adjoint_rhs(cx, C, W, kc, S, delta_w);
   BMPC_SYNC();
+  BMPC_TMARK(15);
   if (ctx_warp(cx) == 0) adjoint_sweep(cx, C, W, S);
   BMPC_SYNC();
+  BMPC_TMARK(16);
   return true;
 }
 

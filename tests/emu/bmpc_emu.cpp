@@ -23,6 +23,7 @@ int emu_solve(const bmpc_config* cfg, int batch, const double* x0, const double*
   work_carve(W, ws.data(), C.N);
   Ctx cx{0, 1, S->red};
   build_tables(cx, C, *S);
+  phase_kin_jacobian_init(cx, C, W);
   for (int b = 0; b < batch; b++) {
     InstanceIO io{x0 + (size_t)b * C.n, p + (size_t)b * C.np, x + (size_t)b * C.n, g + (size_t)b * C.m,
                   lam_g + (size_t)b * C.m, lam_x + (size_t)b * C.n, f + b, kkt + b, iters + b, status + b};
@@ -42,6 +43,7 @@ int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p
   work_carve(W, ws.data(), C.N);
   Ctx cx{0, 1, S->red};
   build_tables(cx, C, *S);
+  phase_kin_jacobian_init(cx, C, W);
   const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
   for (int b = 0; b < batch; b++) {
     EvalIO io{x + b * n, p + (size_t)b * C.np, lam ? lam + b * nl : nullptr, f ? f + b : nullptr, g ? g + (size_t)b * C.m : nullptr,
