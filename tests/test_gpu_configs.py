@@ -1,0 +1,77 @@
+"""BASELINE.json configurations beyond the golden sequences, through the C ABI on the GPU:
+doubled horizon with tightened bounds (configs[3]), the exp2 batch (configs[2]) and the mixed
+batch at bench size (configs[4] shard) with size-independent properties."""
+import numpy as np
+import pytest
+import torch
+from tests.util import rel_q_error
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(N):
+    from boundmpc_b200.ocp import default_solver
+    return default_solver(N=N, nr_segs=4, dt=0.1)
+
+
+def _feasible(r, i, N):
+    g = r["g"][i].reshape(N, 43)
+    return np.abs(g[:, :36]).max() < 1e-7 and g[:, 36:].max() < 1e-7
+
+
+def test_doubled_horizon_tight_bounds_against_oracle():
+    from boundmpc_b200 import batches
+    from oracle import oracle as O
+    N = 20
+    s = _solver(N)
+    assert (s.n, s.m, s.np) == (880, 860, 505)
+    x0, p = batches.make_batch(s, ("exp1",), 0, 48, n=N, tight=True, cache=False, workers=1)
+    r = s.solve_batch(x0, p)
+    ok = r["status"] == 0
+    assert ok.sum() >= 47
+    assert (r["kkt"][ok] <= s.tol).all()
+    for i in np.flatnonzero(ok):
+        assert _feasible(r, i, N)
+    for i in (0, 1, 17, 40):          # cold start, warm starts along the path
+        if not ok[i]:
+            continue
+        ro = O.solve(x0[i], p[i], N=N, tol=s.tol)
+        assert ro["status"] == 0
+        assert rel_q_error(r["x"][i], ro["x"], N) < 1e-6
+        assert abs(r["f"][i] - ro["f"]) < 1e-7 * abs(ro["f"])
+        assert ro["iters"] == r["iters"][i]
+
+
+def test_exp2_batch():
+    from boundmpc_b200 import batches
+    s = _solver(10)
+    x0, p = batches.make_batch(s, ("exp2",), 0, 512, cache=False, workers=4)
+    r = s.solve_batch(x0, p)
+    ok = r["status"] == 0
+    assert ok.mean() >= 0.99
+    assert (r["kkt"][ok] <= s.tol).all()
+    assert all(_feasible(r, i, 10) for i in np.flatnonzero(ok))
+
+
+def test_bench_size_batch_properties():
+    """8,192 mixed instances: convergence rate, KKT error, feasibility in the reference's own sense
+    (BoundMPC.py:461-465), bitwise reproducibility across launches and across batch positions."""
+    from boundmpc_b200 import batches
+    s = _solver(10)
+    B = 8192
+    x0, p = batches.make_batch(s, ("exp1", "exp2"), 0, B, bound_scale=True)
+    xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
+    a = {k: v.clone() for k, v in s.solve_batch(xd, pd).items()}
+    torch.cuda.synchronize()
+    ok = (a["status"] == 0).cpu().numpy()
+    assert ok.mean() >= 0.999
+    assert float(a["kkt"][torch.from_numpy(ok).cuda()].max()) <= s.tol
+    g = a["g"].cpu().numpy()[ok].reshape(-1, 10, 43)
+    viol = np.abs(g[:, :, :36]).clip(1e-6, None).sum(axis=(1, 2)) - 360e-6 + g[:, :, 36:].clip(1e-6, None).sum(axis=(1, 2)) - 70e-6
+    assert viol.max() < 1e-4
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    b = s.solve_batch(xd[perm].contiguous(), pd[perm].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(b["x"], a["x"][perm])          # same instance -> bitwise same solution on any CTA
+    assert torch.equal(b["iters"], a["iters"][perm])
+    assert torch.equal(b["lam_g"], a["lam_g"][perm])
