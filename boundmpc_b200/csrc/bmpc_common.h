@@ -272,6 +272,9 @@ enum {
   R_SIG = R_GJ2 + 8,       // [3][12] Sigma_r = z_r / s_r, 1 / s_r, Sigma_r (d_r + s_r)
   R_SIZE = R_SIG + 3 * ND
 };
+// the part [R_HY, R_SIZE) of a record is produced by the (per-lane serial) path terms; it is staged in
+// shared memory with stride R_PATH and copied out coalesced (see work_attach_smem)
+constexpr int R_PATH = R_SIZE - R_HY;
 // forward-kinematics scratch of one chain evaluation
 enum {
   F_Z = 0,                 // [7][3] joint axes
@@ -283,7 +286,7 @@ enum {
   F_SN = F_POS + 3,        // [7] sin / cos of the joint angles of this evaluation
   F_CS = F_SN + 7,         // [7]
   F_DQ = F_CS + 7,         // [7]
-  F_SIZE = F_DQ + 7
+  F_SIZE = F_DQ + 7 + 1    // (odd stride: the chains of a warp hit different shared-memory banks)
 };
 
 // asynchronous 8-byte copy global -> shared (LDGSTS): issued back to back, completed by cp_async_wait()

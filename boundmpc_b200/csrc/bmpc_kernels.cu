@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 #endif
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  work_attach_smem(W, S, C.N);
   build_tables(cx, C, S);
   phase_kin_jacobian_init(cx, C, W);
   for (;;) {
@@ -75,7 +76,7 @@ static const SolveVariant kVariants[] = {
 #ifdef BMPC_TIMING
     {128, 3, k_solve<128, 3>},
 #else
-    {128, 3, k_solve<128, 3>}, {192, 2, k_solve<192, 2>}, {256, 1, k_solve<256, 1>}, {256, 2, k_solve<256, 2>},
+    {128, 3, k_solve<128, 3>}, {128, 4, k_solve<128, 4>}, {256, 2, k_solve<256, 2>},
 #endif
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant
 #endif
   Work W;
   work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  work_attach_smem(W, S, C.N);
   build_tables(cx, C, S);
   phase_kin_jacobian_init(cx, C, W);
   const size_t n = C.n, nl = (size_t)(NE + ND) * C.N;
@@ -255,6 +257,15 @@ int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes) {
 }
 
 int64_t bmpc_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+
+int bmpc_launch_shape(const bmpc_handle* h, int32_t* threads, int32_t* ctas_per_sm, int32_t* smem_bytes, int32_t* sms) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_launch_shape: null handle");
+  if (threads) *threads = h->threads;
+  if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
+  if (smem_bytes) *smem_bytes = (int32_t)sizeof(Smem);
+  if (sms) *sms = h->sms;
+  return BMPC_OK;
+}
 
 int bmpc_fp64_peak(bmpc_handle* h, int32_t kind, double* flops_per_s) {
   if (!h || !flops_per_s || kind < 0 || kind > 1) return fail(BMPC_E_INVALID, "bmpc_fp64_peak: invalid argument");

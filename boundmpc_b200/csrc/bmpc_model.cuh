@@ -38,7 +38,8 @@ struct Work {
   double *y, *ynew, *c, *ct;                                // [36 N]
   double *s, *st, *zs, *ds, *dzs, *d, *dtr;                 // [12 N]
   double *rec;                                              // [N][R_SIZE]
-  double *fk;                                               // [2 N][F_SIZE]
+  double *fk;                                               // [2 N][F_SIZE] (shared memory when it fits, see work_attach_smem)
+  double *prec; int prec_stride;                            // path part of the records: prec + k * prec_stride + R_x, R_x >= R_HY
   double *Kk;                                               // [N][8*44]
   double *kap;                                              // [N][8]
   double *cost;                                             // [N]
@@ -60,6 +61,7 @@ BMPC_DEV void work_carve(Work& W, double* base, int N) {
   W.d = q; q += nd; W.dtr = q; q += nd;
   W.rec = q; q += (size_t)N * R_SIZE;
   W.fk = q; q += (size_t)2 * N * F_SIZE;
+  W.prec = W.rec; W.prec_stride = R_SIZE;
   W.Kk = q; q += (size_t)N * 8 * NX;
   W.kap = q; q += (size_t)N * 8;
   W.cost = q; q += N;
@@ -406,7 +408,7 @@ BMPC_NOINLINE void path_stage(const int MODE, const Config& C, const double* p, 
 // forward-kinematics chains of warp 0 instead of after them).
 BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq, int mode, int w = 0) {
   ROLE_FOR(k, C.N, w, w + 1) {
-    path_stage(mode, C, p, prev_block(W, x, k), x + NX * k, W.rec + (size_t)k * R_SIZE, d + ND * k, W.cost + k,
+    path_stage(mode, C, p, prev_block(W, x, k), x + NX * k, W.prec + (size_t)k * W.prec_stride, d + ND * k, W.cost + k,
                mode == 2 ? gq + NQ * k : nullptr, W.s + ND * k, W.zs + ND * k);
   }
 }
@@ -418,17 +420,18 @@ BMPC_DEV void phase_path_blocks(const Ctx& cx, const Config& C, const Work& W, c
   PAR_FOR(it, C.N * 80) {
     const int k = it / 80, q = it - 80 * k;
     double* rec = W.rec + (size_t)k * R_SIZE;
-    const double* JD = rec + R_JD;
-    const double* sg = rec + R_SIG;
+    const double* pr = W.prec + (size_t)k * W.prec_stride;
+    const double* JD = pr + R_JD;
+    const double* sg = pr + R_SIG;
     if (q < 64) {
       const int a = q >> 3, b = q & 7;
-      double v = (a < 7 && b < 7) ? rec[R_HY + a * 7 + b] : 0.0;
+      double v = (a < 7 && b < 7) ? pr[R_HY + a * 7 + b] : 0.0;
 #pragma unroll
       for (int r = 0; r < ND; r++) v += sg[r] * JD[r * 8 + a] * JD[r * 8 + b];
-      if (a == 6 && b == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * rec[R_HD + r];
+      if (a == 6 && b == 6) for (int r = 0; r < ND; r++) v += W.zs[ND * k + r] * pr[R_HD + r];
       if (a == 7 && b == 7) {
         double nd = 0.0;
-        for (int m = 0; m < 6; m++) nd += rec[R_DPD + m] * rec[R_DPD + m];
+        for (int m = 0; m < 6; m++) nd += pr[R_DPD + m] * pr[R_DPD + m];
         v += 2 * w2 * nd + 2 * w7;
       }
       rec[R_HYB + q] = v;
@@ -439,6 +442,14 @@ BMPC_DEV void phase_path_blocks(const Ctx& cx, const Config& C, const Work& W, c
 #pragma unroll
       for (int r = 0; r < ND; r++) g += JD[r * 8 + a] * cf[r];
       rec[(q < 72 ? R_GJ1 : R_GJ2) + a] = g;
+    }
+  }
+  // staged path records -> global records (coalesced); HYB / GJ1 / GJ2 were written above
+  if (W.prec != W.rec) {
+    PAR_FOR(it, C.N * (R_HYB - R_HY + 3 * ND)) {
+      const int per = R_HYB - R_HY + 3 * ND, k = it / per, q = it - per * k;
+      const int o = q < R_HYB - R_HY ? R_HY + q : R_SIG + (q - (R_HYB - R_HY));
+      W.rec[(size_t)k * R_SIZE + o] = W.prec[(size_t)k * W.prec_stride + o];
     }
   }
 }
@@ -546,7 +557,7 @@ BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const 
   const double* wt = p + L.w;
   PAR_FOR(it, C.n) {
     const int k = it / NX, i = it - NX * k;
-    const double* rec = W.rec + (size_t)k * R_SIZE;
+    const double* rec = W.prec + (size_t)k * W.prec_stride;
     const double v = x[it];
     double g;
     if (i < 7) g = 2 * BMPC_LDG(wt + 13) * v;
@@ -557,7 +568,7 @@ BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const 
     else if (i < 35) g = rec[R_GY + (i - 29)];
     else if (i < 41) {
       g = rec[R_GV + (i - 35)];
-      if (k + 1 < C.N) g += rec[R_SIZE + R_GVP + (i - 35)];
+      if (k + 1 < C.N) g += rec[W.prec_stride + R_GVP + (i - 35)];
     } else if (i == 41) g = rec[R_GY + 6];
     else g = rec[R_GPH + (i - 42)];
     gradf[it] = g;

@@ -25,9 +25,13 @@ namespace bmpc {
 constexpr int LDM = NX;        // 44
 constexpr int LDY = NZ;        // 52
 constexpr int LDQ = 12;
+constexpr int EV_CAP = NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64 + NX * LDY + 56 * LDQ + (NU * NX + 4);
 struct Smem {
-  double M[48 * LDM];          // W~_kk + P_{k+1}, overwritten by P_k
-  double GKb[2][NK * NZ + 4];  // kinematic rows of G_k = [A_hat | B]; stage k uses buffer k & 1, the other one is prefetched
+  union {
+  double ev[EV_CAP];           // evaluation scratch (kinematic chains, path records) while no Riccati sweep is running
+  struct {
+  double M[NX * LDM];          // W~_kk + P_{k+1}, overwritten by P_k
+  double GK[NK * NZ + 4];      // kinematic rows of G_k = [A_hat | B] (loaded asynchronously during phases 1-2a)
   double Hn[2][4 * 49 + 4];    // HQQN, HQDN, HQQK, HQDK of stage k in buffer k & 1
   double Hc[64 + 8 + NX];      // current stage only: HYB [64], DPD [6], sig [44]
   double ghs[NX];              // g^_k
@@ -35,6 +39,8 @@ struct Smem {
   double YZ[NX * LDY];         // M[:, x] G  (rows 0..7 = u rows "Z", rows 8..43 = x rows "Y")
   double Qu[56 * LDQ];         // columns u_k of Q: rows 0..43 = Q_su, rows 44..51 = Q_uu
   double Ks[NU * NX + 4];      // feedback gain K_k
+  };
+  };
   double pv[NX];               // p_{k+1} / p_k
   double mv[NX];               // g^_k + p_{k+1}
   double tv[NX];               // M[:, x] c + m   (rows 0..7 = u part)
@@ -43,7 +49,7 @@ struct Smem {
   double kapv[NU];
   double odv[6];
   double tcc[NZ * 3];          // constant rows of G per column: coefficients ...
-  int tcr[NZ * 3];             // ... and x-row indices (triv_col as a table)
+  short tcr[NZ * 3 + 4];       // ... and x-row indices (triv_col as a table)
   double alc[5], bec[5];       // d q_n / d(um, q, dq, ddq, u) and d dq_n / d(...) of the integrator (type_coef)
   double red[8 * 8];           // block reductions (8 values x up to 8 warps)
   double filt[2 * 64];         // filter entries (theta, phi)
@@ -52,6 +58,15 @@ struct Smem {
   long long tm[64];
 #endif
 };
+
+// The blocks of the Riccati sweep are idle during the evaluation phases: the forward-kinematics scratch and the
+// path part of the stage records (both written lane by lane, i.e. as scattered 8-byte stores if they lived in
+// global memory) are placed there when they fit (N = 10: both; N = 20: the kinematics scratch only).
+BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N) {
+  int used = 0;
+  if (2 * N * F_SIZE <= EV_CAP) { W.fk = S.ev; used = 2 * N * F_SIZE; }
+  if (used + N * R_PATH <= EV_CAP) { W.prec = S.ev + used - R_HY; W.prec_stride = R_PATH; }
+}
 
 // table form of triv_col, built once per kernel
 BMPC_DEV void build_tables(const Ctx& cx, const Config& C, Smem& S) {
@@ -195,11 +210,16 @@ BMPC_DEV void kkt_prepare(const Ctx& cx, const Config& C, const Work& W, double 
 
 // Stage data of the backward sweep is staged in shared memory one stage ahead (stage_prefetch runs
 // in the gain phase of stage k + 1, on the warps that have no column to solve).
+// kinematic rows of stage k into S.GK (single buffer: issued after the last reader of stage k + 1's rows, the
+// P update, has passed its barrier; first needed by phase 2b)
+BMPC_DEV void gk_load(const Ctx& cx, const Work& W, Smem& S, int k) {
+  const double* src = W.rec + (size_t)k * R_SIZE + R_GK;
+  PAR_FOR(i, NK * NZ) cp_async8(S.GK + i, src + i);
+}
+
 BMPC_DEV void stage_prefetch(const Ctx& cx, const Config& C, const Work& W, Smem& S, int k, int w0, int w1) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
-  double* GK = S.GKb[k & 1];
   double* Hk = S.Hn[k & 1];
-  ROLE_FOR(i, NK * NZ, w0, w1) cp_async8(GK + i, rec + R_GK + i);
   ROLE_FOR(i, 4 * 49, w0, w1) cp_async8(Hk + i, rec + R_HQQN + i);
   ROLE_FOR(i, 64, w0, w1) cp_async8(S.Hc + i, rec + R_HYB + i);
   ROLE_FOR(i, 6, w0, w1) cp_async8(S.Hc + 64 + i, rec + R_DPD + i);
@@ -309,10 +329,11 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 // the pass (mma_rowblock: A fragments shared by the tiles of a row block).
 BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const bool first = k == 0;      // stage 0: the previous block is fixed -> only the u-columns
-  const double* GKs = S.GKb[k & 1];
+  const double* GKs = S.GK;
   const double* Hk = S.Hn[k & 1];
   const int nw = ctx_nwarps(cx);
   // ---- phase 1: M = P_{k+1} + W~_kk + delta_w I
+  gk_load(cx, W, S, k);
   add_W(cx, C, kc, S, k, delta_w);
   PAR_FOR(i, NX) S.mv[i] = S.ghs[i] + S.pv[i];
   PAR_FOR(m, 6) S.odv[m] = 2 * kc.w5 * S.Hc[64 + m] * kc.idt;
@@ -337,13 +358,14 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
     for (int l = 0; l < NE; l += 4) { a0 += Mr[l] * S.cv[l]; a1 += Mr[l + 1] * S.cv[l + 1]; a2 += Mr[l + 2] * S.cv[l + 2]; a3 += Mr[l + 3] * S.cv[l + 3]; }
     S.tv[i] = (a0 + a1) + (a2 + a3);
   }
+  cp_async_wait();   // S.GK
   BMPC_SYNC();
   BMPC_TMARK(9);
   // ---- phase 2b: YZ += M[:, kin] GK: 6 row blocks x (4 + 3) column tiles, 3 k-steps
   for (int per = (12 + nw - 1) / nw, t = ctx_warp(cx) * per; t < 12 && t < (ctx_warp(cx) + 1) * per; t++) {
     const int ti = t >> 1, tj0 = (t & 1) ? 4 : 0, nt = (t & 1) ? 3 : 4;
     mma_rowblock<3, 4>(cx, nt,
-        [&](int r, int kk) { return S.M[(8 * ti + r) * LDM + 8 + rKIN + kk]; },
+        [&](int r, int kk) { const int i = 8 * ti + r; return S.M[(i < NX ? i : NX - 1) * LDM + 8 + rKIN + kk]; },   // (rows >= 44 of the last row block are discarded)
         [&](int tt, int kk, int c) { return GKs[kk * NZ + 8 * (tj0 + tt) + c]; },
         [&](int tt, int r, int c) { const int i = 8 * ti + r, col = 8 * (tj0 + tt) + c; return (i < NX && col < NZ) ? S.YZ[i * LDY + col] : 0.0; },
         [&](int tt, int r, int c, double v) { const int i = 8 * ti + r, col = 8 * (tj0 + tt) + c; if (i < NX && col < NZ) S.YZ[i * LDY + col] = v; });

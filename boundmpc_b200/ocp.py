@@ -95,6 +95,12 @@ class BatchSolver:
     def launch_count(self):
         return int(self._lib.bmpc_launch_count(self._h))
 
+    def launch_shape(self):
+        """threads per CTA, resident CTAs per SM, shared memory per CTA [B], SM count of the solver kernel."""
+        v = [ctypes.c_int32() for _ in range(4)]
+        _cabi.check(self._lib.bmpc_launch_shape(self._h, *[ctypes.byref(x) for x in v]), "bmpc_launch_shape")
+        return {"threads": v[0].value, "ctas_per_sm": v[1].value, "smem_bytes": v[2].value, "sms": v[3].value}
+
     def fp64_peak(self, kind=0):
         """Measured FP64 rate of the device in FLOP/s: kind 0 = DFMA loop, 1 = DMMA (mma.sync m8n8k4) loop."""
         v = ctypes.c_double()

@@ -102,6 +102,10 @@ int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const d
  * number of kernel launches issued by this library since the handle was created */
 int64_t bmpc_launch_count(const bmpc_handle* h);
 
+/* launch shape of the solver kernel chosen by bmpc_create (diagnostics / bench config): threads per CTA,
+ * resident CTAs per SM (occupancy-checked), dynamic shared memory per CTA in bytes, number of SMs */
+int bmpc_launch_shape(const bmpc_handle* h, int32_t* threads, int32_t* ctas_per_sm, int32_t* smem_bytes, int32_t* sms);
+
 /* Diagnostics for bench.py's roofline denominator (MEASURED_PEAKS.json has no FP64
  * entry): runs a register-resident DFMA loop (kind 0) or an mma.sync.m8n8k4.f64 DMMA loop
  * (kind 1) on every SM of the handle's device and returns the sustained rate in FLOP/s. */

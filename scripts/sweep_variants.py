@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 base = default_solver()
 x0, p = batches.make_batch(base, ("exp1", "exp2"), 0, B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
-for threads, ctas in [(128, 3), (192, 2), (256, 1), (256, 2)]:
+for threads, ctas in [(128, 4), (128, 3), (256, 2)]:
     os.environ["BMPC_THREADS"], os.environ["BMPC_CTAS_PER_SM"] = str(threads), str(ctas)
     try:
         s = default_solver()
@@ -22,4 +22,4 @@ for threads, ctas in [(128, 3), (192, 2), (256, 1), (256, 2)]:
         e0.record(); s.solve_batch(xd, pd, out); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     print(json.dumps({"threads": threads, "ctas_per_sm": ctas, "B": B, "ms": best, "solves_per_s": B / best * 1e3,
-                      "ok": int((out["status"] == 0).sum()), "iters_mean": float(out["iters"].double().mean())}), flush=True)
+                      "shape": s.launch_shape(), "ok": int((out["status"] == 0).sum()), "iters_mean": float(out["iters"].double().mean())}), flush=True)

@@ -21,6 +21,7 @@ int emu_solve(const bmpc_config* cfg, int batch, const double* x0, const double*
   Smem* S = new Smem;
   Work W;
   work_carve(W, ws.data(), C.N);
+  work_attach_smem(W, *S, C.N);
   Ctx cx{0, 1, S->red};
   build_tables(cx, C, *S);
   phase_kin_jacobian_init(cx, C, W);
@@ -41,6 +42,7 @@ int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p
   Smem* S = new Smem;
   Work W;
   work_carve(W, ws.data(), C.N);
+  work_attach_smem(W, *S, C.N);
   Ctx cx{0, 1, S->red};
   build_tables(cx, C, *S);
   phase_kin_jacobian_init(cx, C, W);
