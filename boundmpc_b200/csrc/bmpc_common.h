@@ -60,10 +60,10 @@ struct Ctx {
   long long* tm;  // [64] per-phase cycles, [63] = last time stamp
 #endif
 };
-BMPC_DEV int ctx_warp(const Ctx& cx) { return cx.tid >> 5; }
-BMPC_DEV int ctx_nwarps(const Ctx& cx) { return (cx.nt + 31) >> 5; }
+BMPC_DEV int ctx_warp(const Ctx cx) { return cx.tid >> 5; }
+BMPC_DEV int ctx_nwarps(const Ctx cx) { return (cx.nt + 31) >> 5; }
 // is this thread in warps [w0, w1)?  (host emulation: the single thread plays every role)
-BMPC_DEV bool in_role(const Ctx& cx, int w0, int w1) {
+BMPC_DEV bool in_role(const Ctx cx, int w0, int w1) {
 #ifdef BMPC_HOST_EMU
   (void)cx; (void)w0; (void)w1;
   return true;
@@ -79,7 +79,7 @@ BMPC_DEV bool in_role(const Ctx& cx, int w0, int w1) {
 // Fragment layout (PTX ISA, m8n8k4 .f64): lane l holds A(l / 4, l % 4), B(l % 4, l / 4) and
 // C(l / 4, 2 (l % 4) + {0, 1}).  The host-emulation build evaluates the same tile with loops.
 template <class FA, class FB, class FE>
-BMPC_DEV void mma_tile(const Ctx& cx, int ksteps, FA a, FB b, FE epi) {
+BMPC_DEV void mma_tile(const Ctx cx, int ksteps, FA a, FB b, FE epi) {
 #ifdef BMPC_HOST_EMU
   (void)cx;
   for (int r = 0; r < 8; r++)
@@ -105,7 +105,7 @@ BMPC_DEV void mma_tile(const Ctx& cx, int ksteps, FA a, FB b, FE epi) {
 // executed by one warp; the A fragments are loaded once, C starts from cin (a previous pass) and
 // every element is handed to epi(t, r, c, value) exactly once.
 template <int KS, int NT, class FA, class FB, class FC, class FE>
-BMPC_DEV void mma_rowblock(const Ctx& cx, int nt, FA a, FB b, FC cin, FE epi) {
+BMPC_DEV void mma_rowblock(const Ctx cx, int nt, FA a, FB b, FC cin, FE epi) {
 #ifdef BMPC_HOST_EMU
   (void)cx;
   for (int t = 0; t < nt; t++)
@@ -150,7 +150,7 @@ BMPC_DEV void mma_rowblock(const Ctx& cx, int nt, FA a, FB b, FC cin, FE epi) {
 // Column block of tiles that share their B fragments: C_t(r, c) = sum_{kk < 4 KS} a(t, r, kk) * b(kk, c) for
 // t < nt (<= NT); same interleaving of the independent accumulators as mma_rowblock.
 template <int KS, int NT, class FA, class FB, class FE>
-BMPC_DEV void mma_colblock(const Ctx& cx, int nt, FA a, FB b, FE epi) {
+BMPC_DEV void mma_colblock(const Ctx cx, int nt, FA a, FB b, FE epi) {
 #ifdef BMPC_HOST_EMU
   (void)cx;
   for (int t = 0; t < nt; t++)
@@ -321,7 +321,7 @@ BMPC_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[
 enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
 
 // (one copy in the kernel image: K and the operations are run-time arguments)
-BMPC_NOINLINE void block_reduce_n(const Ctx& cx, double* v, const int* op, int K) {
+BMPC_NOINLINE void block_reduce_n(const Ctx cx, double* v, const int* op, int K) {
 #ifndef BMPC_HOST_EMU
   const int lane = cx.tid & 31, warp = cx.tid >> 5, nw = (cx.nt + 31) >> 5;
 #pragma unroll 1
@@ -352,7 +352,7 @@ BMPC_NOINLINE void block_reduce_n(const Ctx& cx, double* v, const int* op, int K
 #endif
 }
 template <int K>
-BMPC_DEV void block_reduce(const Ctx& cx, double (&v)[K], const int (&op)[K]) { block_reduce_n(cx, v, op, K); }
+BMPC_DEV void block_reduce(const Ctx cx, double (&v)[K], const int (&op)[K]) { block_reduce_n(cx, v, op, K); }
 
 // status codes returned per instance
 enum { ST_SUCCESS = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_NUMERIC = 4 };

@@ -12,7 +12,7 @@ struct EvalIO {
   double *f, *g, *d, *grad, *jac, *hess;   // may be null
 };
 
-BMPC_DEV void eval_instance(const Ctx& cx, const Config& C, const Work& W, Smem& S, const EvalIO& io) {
+BMPC_DEV void eval_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const EvalIO& io) {
   const int N = C.N, n = C.n;
   build_wp0(cx, C, io.p, W.wp0);
   PAR_FOR(i, n) { W.x[i] = io.x[i]; W.zL[i] = 0.0; W.zU[i] = 0.0; }

@@ -34,7 +34,7 @@ struct InstanceIO {
 
 BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 
-BMPC_DEV void solve_instance(const Ctx& cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io) {
+BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io) {
   const int N = C.N, n = C.n, ne = NE * N, nd = ND * N;
   const double* p = io.p;
   // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)

@@ -38,7 +38,7 @@ extern "C" int bmpc_phase_cycles(unsigned long long* out, int reset) {
 #endif
 
 template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C, int batch, BatchIO io, double* ws,
+__global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C0, int batch, BatchIO io, double* ws,
                                                          size_t ws_stride, unsigned int* counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -49,9 +49,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 #else
   Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
 #endif
-  Work W;
-  work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
-  work_attach_smem(W, S, C.N);
+  if (threadIdx.x == 0) {
+    S.cfg = C0;
+    work_carve(S.work, ws + (size_t)blockIdx.x * ws_stride, C0.N);
+    work_attach_smem(S.work, S, C0.N);
+  }
+  __syncthreads();
+  const Config& C = S.cfg;
+  const Work& W = S.work;
   build_tables(cx, C, S);
   phase_kin_jacobian_init(cx, C, W);
   for (;;) {

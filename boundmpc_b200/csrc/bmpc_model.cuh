@@ -70,7 +70,7 @@ BMPC_DEV void work_carve(Work& W, double* base, int N) {
 }
 
 // previous-stage block of stage 0: u_{-1}, x_0 come from the parameter vector (App. A.4)
-BMPC_DEV void build_wp0(const Ctx& cx, const Config& C, const double* p, double* wp) {
+BMPC_DEV void build_wp0(const Ctx cx, const Config& C, const double* p, double* wp) {
   const PLayout& L = C.L;
   PAR_FOR(i, NX) {
     double v = 0.0;
@@ -90,7 +90,7 @@ BMPC_DEV const double* prev_block(const Work& W, const double* x, int k) { retur
 // ---------------------------------------------------------------------------------------------
 // Phase 1: one-step integration with piecewise-linear jerk (bound_mpc_functions.py:254-260,
 // jerk_trajectory_casadi.py at t = h) -> linear residual rows and the chain inputs
-BMPC_DEV void phase_integrate(const Ctx& cx, const Config& C, const Work& W, const double* x, double* c) {
+BMPC_DEV void phase_integrate(const Ctx cx, const Config& C, const Work& W, const double* x, double* c) {
   PAR_FOR(it, C.N * 8) {
     const int k = it >> 3, j = it & 7;
     const double* wp = prev_block(W, x, k);
@@ -167,14 +167,14 @@ BMPC_NOINLINE void fk_chain(double* f) {
   }
 }
 
-BMPC_DEV void phase_fk(const Ctx& cx, const Config& C, const Work& W) {
+BMPC_DEV void phase_fk(const Ctx cx, const Config& C, const Work& W) {
   ROLE_FOR(it, 2 * C.N, 0, 1) fk_chain(W.fk + (size_t)it * F_SIZE);
 }
 
 // Phase 3a: kinematic residual rows 21..32 (casadi_ocp_formulation.py:284-291,
 // bound_mpc_functions.py:262-282: p_pos = fk_pos(q_n), v = [velocity_ee; omega_ee](q_n, dq_n),
 // trapezoidal integration of omega into p_rot)
-BMPC_DEV void phase_kin_residual(const Ctx& cx, const Config& C, const Work& W, const double* x, double* c) {
+BMPC_DEV void phase_kin_residual(const Ctx cx, const Config& C, const Work& W, const double* x, double* c) {
   PAR_FOR(it, C.N * 3) {
     const int k = it / 3, i = it - 3 * k;
     const double* wp = prev_block(W, x, k);
@@ -406,7 +406,7 @@ BMPC_NOINLINE void path_stage(const int MODE, const Config& C, const double* p, 
 
 // One item per stage, dealt to the lanes of warp `w` (long serial items: they run next to the
 // forward-kinematics chains of warp 0 instead of after them).
-BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq, int mode, int w = 0) {
+BMPC_DEV void phase_path(const Ctx cx, const Config& C, const Work& W, const double* p, const double* x, double* d, double* gq, int mode, int w = 0) {
   ROLE_FOR(k, C.N, w, w + 1) {
     path_stage(mode, C, p, prev_block(W, x, k), x + NX * k, W.prec + (size_t)k * W.prec_stride, d + ND * k, W.cost + k,
                mode == 2 ? gq + NQ * k : nullptr, W.s + ND * k, W.zs + ND * k);
@@ -415,7 +415,7 @@ BMPC_DEV void phase_path(const Ctx& cx, const Config& C, const Work& W, const do
 
 // y-block of the condensed Hessian, HYB = HY + z.HD + J_d^T Sigma_s J_d + dphi tracking term, and the
 // slack part of g^ (Sigma_r = z_r / s_r); 80 independent items per stage, run after path_stage<1>.
-BMPC_DEV void phase_path_blocks(const Ctx& cx, const Config& C, const Work& W, const double* p) {
+BMPC_DEV void phase_path_blocks(const Ctx cx, const Config& C, const Work& W, const double* p) {
   const double w2 = BMPC_LDG(p + C.L.w + 2), w7 = BMPC_LDG(p + C.L.w + 7);
   PAR_FOR(it, C.N * 80) {
     const int k = it / 80, q = it - 80 * k;
@@ -459,7 +459,7 @@ BMPC_DEV void phase_path_blocks(const Ctx& cx, const Config& C, const Work& W, c
 // (integrated state) the scalar is
 //   Phi = lam_p . fk_pos + lam_v . (Jv dq) + (lam_w + h/2 lam_rot) . (Jw dq)
 // and for ch = 2k+1 (stage variables) it is  h/2 lam_rot . Jw(q_k) dq_k  (SURVEY App. A.7).
-BMPC_DEV void phase_kin_hessian(const Ctx& cx, const Config& C, const Work& W) {
+BMPC_DEV void phase_kin_hessian(const Ctx cx, const Config& C, const Work& W) {
   PAR_FOR(it, 2 * C.N * 49) {
     const int ch = it / 49, ij = it - 49 * ch, i = ij / 7, j = ij - 7 * i;
     const int k = ch >> 1, which = ch & 1;
@@ -507,7 +507,7 @@ BMPC_DEV void phase_kin_hessian(const Ctx& cx, const Config& C, const Work& W) {
 //   d pos / dq_i = z_i x r_i ;  d(Jv dq)/dq_i = z_i x W_i + Om_{<i} x (z_i x r_i) ;  d(Jw dq)/dq_i = z_i x Om_{>i}
 // Structural zeros and the identity of the p_rot columns of GK: the sparsity pattern never changes, so this
 // runs once per CTA workspace (kernel start), not per evaluation.
-BMPC_DEV void phase_kin_jacobian_init(const Ctx& cx, const Config& C, const Work& W) {
+BMPC_DEV void phase_kin_jacobian_init(const Ctx cx, const Config& C, const Work& W) {
   PAR_FOR(it, C.N * NZ) {
     const int k = it / NZ, col = it - NZ * k;
     double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
@@ -515,7 +515,7 @@ BMPC_DEV void phase_kin_jacobian_init(const Ctx& cx, const Config& C, const Work
     if (col >= oPROT && col < oPROT + 3) GK[(3 + col - oPROT) * NZ + col] = 1.0;
   }
 }
-BMPC_DEV void phase_kin_jacobian(const Ctx& cx, const Config& C, const Work& W) {
+BMPC_DEV void phase_kin_jacobian(const Ctx cx, const Config& C, const Work& W) {
   PAR_FOR(it, C.N * 7) {
     const int k = it / 7, j = it - 7 * k;
     const double* f0 = W.fk + (size_t)(2 * k) * F_SIZE;
@@ -552,7 +552,7 @@ BMPC_DEV void phase_kin_jacobian(const Ctx& cx, const Config& C, const Work& W) 
 }
 
 // Phase 6: gradient of the objective (nlp_grad_f)
-BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* gradf) {
+BMPC_DEV void phase_grad_f(const Ctx cx, const Config& C, const Work& W, const double* p, const double* x, double* gradf) {
   const PLayout& L = C.L;
   const double* wt = p + L.w;
   PAR_FOR(it, C.n) {
@@ -579,7 +579,7 @@ BMPC_DEV void phase_grad_f(const Ctx& cx, const Config& C, const Work& W, const 
 // Whole-horizon evaluation.  full = derivative records too (needs the current multipliers in W.y).
 // The two long serial pieces — the kinematic chains (2 N lanes of warp 0) and the path terms (N lanes
 // of warp 1) — run side by side; everything else is dealt to all threads.
-BMPC_NOINLINE void eval_values(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x, double* c, double* d) {
+BMPC_NOINLINE void eval_values(const Ctx cx, const Config& C, const Work& W, const double* p, const double* x, double* c, double* d) {
   phase_integrate(cx, C, W, x, c);
   BMPC_SYNC();
   BMPC_TMARK(3);
@@ -592,7 +592,7 @@ BMPC_NOINLINE void eval_values(const Ctx& cx, const Config& C, const Work& W, co
   BMPC_TMARK(5);
 }
 
-BMPC_NOINLINE void eval_full(const Ctx& cx, const Config& C, const Work& W, const double* p, const double* x) {
+BMPC_NOINLINE void eval_full(const Ctx cx, const Config& C, const Work& W, const double* p, const double* x) {
   phase_integrate(cx, C, W, x, W.c);
   BMPC_SYNC();
   BMPC_TMARK(0);

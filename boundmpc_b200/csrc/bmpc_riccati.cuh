@@ -25,6 +25,8 @@ namespace bmpc {
 constexpr int LDM = NX;        // 44
 constexpr int LDY = NZ;        // 52
 constexpr int LDQ = 12;
+constexpr int VEC_NMAX = 10, VEC_CAP = VEC_NMAX * (3 * NX + NE + 2 * ND);
+constexpr int EV_STEP0 = NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64 + 256;   // offset of YZ[256] in ev
 constexpr int EV_CAP = NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64 + NX * LDY + 56 * LDQ + (NU * NX + 4);
 struct Smem {
   union {
@@ -41,6 +43,9 @@ struct Smem {
   double Ks[NU * NX + 4];      // feedback gain K_k
   };
   };
+  double vec[VEC_CAP];         // iterate of the interior-point method (x, y, s, z_s, z_L, z_U) for N <= 10
+  Config cfg;                  // copies of the kernel parameter and of the workspace pointers: the large phase bodies are
+  Work work;                   // real functions and take them by reference; these copies keep those reads on chip
   double pv[NX];               // p_{k+1} / p_k
   double mv[NX];               // g^_k + p_{k+1}
   double tv[NX];               // M[:, x] c + m   (rows 0..7 = u part)
@@ -66,10 +71,21 @@ BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N) {
   int used = 0;
   if (2 * N * F_SIZE <= EV_CAP) { W.fk = S.ev; used = 2 * N * F_SIZE; }
   if (used + N * R_PATH <= EV_CAP) { W.prec = S.ev + used - R_HY; W.prec_stride = R_PATH; }
+  if (N <= VEC_NMAX) {
+    // the iterate lives in shared memory for the whole solve ...
+    const int n = NX * N, ne = NE * N, nd = ND * N;
+    double* q = S.vec;
+    W.x = q; q += n; W.zL = q; q += n; W.zU = q; q += n; W.y = q; q += ne; W.s = q; q += nd; W.zs = q; q += nd;
+    // ... and the step / trial vectors sit behind the sweep scratch (YZ[0..256)) of the Riccati blocks: they are
+    // written by the forward / adjoint sweeps after the backward pass and are dead before the next one starts
+    q = S.ev + EV_STEP0;
+    W.dx = q; q += n; W.dzL = q; q += n; W.dzU = q; q += n; W.xt = q; q += n; W.ynew = q; q += ne; W.ct = q; q += ne;
+    W.ds = q; q += nd; W.dzs = q; q += nd; W.st = q; q += nd; W.dtr = q; q += nd;
+  }
 }
 
 // table form of triv_col, built once per kernel
-BMPC_DEV void build_tables(const Ctx& cx, const Config& C, Smem& S) {
+BMPC_DEV void build_tables(const Ctx cx, const Config& C, Smem& S) {
   PAR_FOR(col, NZ) {
     int rr[3]; double cf[3];
     const int nt = triv_col(C, col, rr, cf);
@@ -193,7 +209,7 @@ BMPC_DEV double ou_entry(const double* H, const double* al, const double* be, in
 
 // Once per interior-point iteration: bound part of the barrier Hessian (W.sig) and the gradient g^ of
 // the barrier problem without the equality multipliers (W.gh).
-BMPC_DEV void kkt_prepare(const Ctx& cx, const Config& C, const Work& W, double mu) {
+BMPC_DEV void kkt_prepare(const Ctx cx, const Config& C, const Work& W, double mu) {
   PAR_FOR(gi, C.n) {
     const int k = gi / NX, a = gi - NX * k;
     double gb = W.gradf[gi], sg = 0.0;
@@ -212,12 +228,12 @@ BMPC_DEV void kkt_prepare(const Ctx& cx, const Config& C, const Work& W, double 
 // in the gain phase of stage k + 1, on the warps that have no column to solve).
 // kinematic rows of stage k into S.GK (single buffer: issued after the last reader of stage k + 1's rows, the
 // P update, has passed its barrier; first needed by phase 2b)
-BMPC_DEV void gk_load(const Ctx& cx, const Work& W, Smem& S, int k) {
+BMPC_DEV void gk_load(const Ctx cx, const Work& W, Smem& S, int k) {
   const double* src = W.rec + (size_t)k * R_SIZE + R_GK;
   PAR_FOR(i, NK * NZ) cp_async8(S.GK + i, src + i);
 }
 
-BMPC_DEV void stage_prefetch(const Ctx& cx, const Config& C, const Work& W, Smem& S, int k, int w0, int w1) {
+BMPC_DEV void stage_prefetch(const Ctx cx, const Config& C, const Work& W, Smem& S, int k, int w0, int w1) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
   double* Hk = S.Hn[k & 1];
   ROLE_FOR(i, 4 * 49, w0, w1) cp_async8(Hk + i, rec + R_HQQN + i);
@@ -233,7 +249,7 @@ BMPC_DEV void stage_prefetch(const Ctx& cx, const Config& C, const Work& W, Smem
 // y-block; the remaining diagonal; the velocity / acceleration tracking cross terms.  Every entry of
 // S.M is touched by at most one item.
 constexpr int W_ITEMS = 49 + 64 + 8 + 24;
-BMPC_DEV void add_W(const Ctx& cx, const Config& C, const KktCoef& kc, Smem& S, int k, double delta_w) {
+BMPC_DEV void add_W(const Ctx cx, const Config& C, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const double* Hk = S.Hn[k & 1];          // HQQN 0, HQDN 49, HQQK 98, HQDK 147
   const double* Hx = S.Hn[(k + 1) & 1];    // same of stage k + 1
   const double* dpd = S.Hc + 64;
@@ -327,7 +343,7 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 // Every product with G = [A_hat | B] is split into the constant integrator rows (a cheap pass, see
 // triv_combine) and the 12 dense kinematic rows, which run as 8 x 8 DMMA tiles on top of the result of
 // the pass (mma_rowblock: A fragments shared by the tiles of a row block).
-BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
+BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const KktCoef& kc, Smem& S, int k, double delta_w) {
   const bool first = k == 0;      // stage 0: the previous block is fixed -> only the u-columns
   const double* GKs = S.GK;
   const double* Hk = S.Hn[k & 1];
@@ -521,7 +537,7 @@ BMPC_DEV bool riccati_stage(const Ctx& cx, const Config& C, const Work& W, const
 
 // Forward sweep, executed by ONE warp (no CTA barriers inside): du_k = kappa_k + K_k ds_k,
 // dx_{k+1} = G_k (ds_k, du_k) + c_k.  The running (ds, du) vector lives in shared memory.
-BMPC_DEV void forward_sweep(const Ctx& cx, const Config& C, const Work& W, Smem& S) {
+BMPC_DEV void forward_sweep(const Ctx cx, const Config& C, const Work& W, Smem& S) {
   double* zb = S.YZ;            // [2][64]: z = (ds (44), du (8)) of the current / next stage
   double* part = S.YZ + 128;    // [32] partial sums
   LANE_FOR(l, 128) zb[l] = 0.0;
@@ -569,7 +585,7 @@ BMPC_DEV void forward_sweep(const Ctx& cx, const Config& C, const Work& W, Smem&
 //   r_k = [W~_kk dw_k + O_k dw_{k-1} + O_{k+1}^T dw_{k+1} + g^_k]_x
 // with the products taken block by block from the stage records (see add_W).  The curvature part
 // uses d q_n = dw_{k+1}[q] - c_{k+1}[q rows] (the linearised change of the integrated state).
-BMPC_DEV void adjoint_rhs(const Ctx& cx, const Config& C, const Work& W, const KktCoef& kc, const Smem& S, double delta_w) {
+BMPC_DEV void adjoint_rhs(const Ctx cx, const Config& C, const Work& W, const KktCoef& kc, const Smem& S, double delta_w) {
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
   PAR_FOR(it, C.N * NE) {
     const int k = it / NE, r = 8 + it - NE * k;
@@ -616,7 +632,7 @@ BMPC_DEV void adjoint_rhs(const Ctx& cx, const Config& C, const Work& W, const K
 }
 
 // Adjoint recursion y_k = r_k + [A_hat_{k+1}^T y_{k+1}]_x, executed by ONE warp.
-BMPC_DEV void adjoint_sweep(const Ctx& cx, const Config& C, const Work& W, Smem& S) {
+BMPC_DEV void adjoint_sweep(const Ctx cx, const Config& C, const Work& W, Smem& S) {
   double* yb = S.YZ;            // [2][40]
   const int N = C.N;
   LANE_FOR(i, NE) yb[40 * ((N - 1) & 1) + i] = W.ynew[NE * (N - 1) + i];
@@ -636,7 +652,7 @@ BMPC_DEV void adjoint_sweep(const Ctx& cx, const Config& C, const Work& W, Smem&
 
 // Backward + forward + adjoint sweeps: dx (primal step) and ynew (equality multipliers of the full
 // step).  kkt_prepare must have run for the current iterate.
-BMPC_NOINLINE bool kkt_solve(const Ctx& cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
+BMPC_NOINLINE bool kkt_solve(const Ctx cx, const Config& C, const Work& W, const double* p, Smem& S, double delta_w) {
   const KktCoef kc = kkt_coef(C, p);
   PAR_FOR(i, NX * NX) S.M[i] = 0.0;
   PAR_FOR(i, NX) S.pv[i] = 0.0;
