@@ -171,7 +171,8 @@ def main():
               "instances_per_gpu": per_gpu, "total_instances": per_gpu * max(1, world), "horizon_N": 10, "nr_segs": 4,
               "n_var": n, "n_con": m, "tol": TOL,
               "l2": f"inputs+outputs {per_gpu * IO_BYTES[10] / 1e6:.0f} MB per step (> 126 MB L2), no explicit flush",
-              "parallelism": f"independent instances, contiguous shards over {max(1, world)} GPU(s)"}
+              "parallelism": f"independent instances, contiguous shards over {max(1, world)} GPU(s)",
+              "launch_shape": solver.launch_shape()}
 
     # ------------------------------------------------------------------ reference arm (CPU restatement)
     if args.impl == "reference":

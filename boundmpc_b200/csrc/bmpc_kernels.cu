@@ -81,7 +81,7 @@ static const SolveVariant kVariants[] = {
 #ifdef BMPC_TIMING
     {128, 3, k_solve<128, 3>},
 #else
-    {128, 3, k_solve<128, 3>}, {128, 4, k_solve<128, 4>}, {256, 2, k_solve<256, 2>},
+    {128, 3, k_solve<128, 3>}, {160, 3, k_solve<160, 3>}, {192, 3, k_solve<192, 3>}, {256, 2, k_solve<256, 2>},
 #endif
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);

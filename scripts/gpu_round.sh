@@ -11,5 +11,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_solve -s 2 -c 1 -o gpurun_out/prof_k_solve \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --per-gpu 2048 > gpurun_out/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
