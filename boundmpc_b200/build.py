@@ -23,14 +23,15 @@ def needs_build():
 TIMING_LIB = os.path.join(HERE, "libboundmpc_b200_timing.so")   # development build with per-phase cycle counters
 
 
-def build(force=False, verbose=False, timing=False):
-    if timing:
+def build(force=False, verbose=False, timing=False, defines=(), out=None):
+    if timing or out:
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-DBMPC_TIMING", "-o", TIMING_LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        target = out or TIMING_LIB
+        cmd = [nvcc] + NVCC_FLAGS + (["-DBMPC_TIMING"] if timing else []) + ["-D" + d for d in defines] + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        return TIMING_LIB
+        return target
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -44,4 +45,6 @@ def build(force=False, verbose=False, timing=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, timing="--timing" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=True, timing="--timing" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -215,6 +215,9 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->variant = -1;
   for (int v = 0; v < kNumVariants; v++)
     if (kVariants[v].threads == want_t && kVariants[v].minb == want_c) h->variant = v;
+  // fewer resident CTAs than a variant was compiled for: same kernel, smaller grid (occupancy experiments)
+  for (int v = 0; v < kNumVariants && h->variant < 0; v++)
+    if (kVariants[v].threads == want_t && kVariants[v].minb > want_c && want_c >= 1) h->variant = v;
   if (h->variant < 0) { delete h; return fail(BMPC_E_INVALID, "bmpc_create: no kernel variant for this threads / CTAs-per-SM combination"); }
   h->threads = want_t;
   e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -230,17 +230,27 @@ BMPC_DEV void kkt_prepare(const Ctx cx, const Config& C, const Work& W, double m
 // P update, has passed its barrier; first needed by phase 2b)
 BMPC_DEV void gk_load(const Ctx cx, const Work& W, Smem& S, int k) {
   const double* src = W.rec + (size_t)k * R_SIZE + R_GK;
+#pragma unroll 1
   PAR_FOR(i, NK * NZ) cp_async8(S.GK + i, src + i);
 }
 
 BMPC_DEV void stage_prefetch(const Ctx cx, const Config& C, const Work& W, Smem& S, int k, int w0, int w1) {
   const double* rec = W.rec + (size_t)k * R_SIZE;
   double* Hk = S.Hn[k & 1];
-  ROLE_FOR(i, 4 * 49, w0, w1) cp_async8(Hk + i, rec + R_HQQN + i);
-  ROLE_FOR(i, 64, w0, w1) cp_async8(S.Hc + i, rec + R_HYB + i);
-  ROLE_FOR(i, 6, w0, w1) cp_async8(S.Hc + 64 + i, rec + R_DPD + i);
-  ROLE_FOR(i, NX, w0, w1) { cp_async8(S.Hc + 72 + i, W.sig + NX * k + i); cp_async8(S.ghs + i, W.gh + NX * k + i); }
-  ROLE_FOR(i, NE, w0, w1) cp_async8(S.cv + i, W.c + NE * k + i);
+  // one rolled loop over the 390 doubles of the stage (code size: this runs once per stage inside the sweep)
+  constexpr int n0 = 4 * 49, n1 = n0 + 64, n2 = n1 + 6, n3 = n2 + NX, n4 = n3 + NX, n5 = n4 + NE;
+#pragma unroll 1
+  ROLE_FOR(i, n5, w0, w1) {
+    const double* src;
+    double* dst;
+    if (i < n0) { src = rec + R_HQQN + i; dst = Hk + i; }
+    else if (i < n1) { src = rec + R_HYB + (i - n0); dst = S.Hc + (i - n0); }
+    else if (i < n2) { src = rec + R_DPD + (i - n1); dst = S.Hc + 64 + (i - n1); }
+    else if (i < n3) { src = W.sig + NX * k + (i - n2); dst = S.Hc + 72 + (i - n2); }
+    else if (i < n4) { src = W.gh + NX * k + (i - n3); dst = S.ghs + (i - n3); }
+    else { src = W.c + NE * k + (i - n4); dst = S.cv + (i - n4); }
+    cp_async8(dst, src);
+  }
 }
 
 // S.M += W~_kk + delta_w I, added block by block from the staged stage records (the 44 x 44 block is

@@ -40,7 +40,7 @@ typedef struct bmpc_config {
   double dq_lim_lower[7], dq_lim_upper[7];
   double tol;           /* termination tolerance on Ipopt's scaled error (<= 0: 1e-9) */
   int32_t max_iter;     /* <= 0: 500 (BoundMPC.py:122) */
-  double mu_init;       /* <= 0: 0.1 */
+  double mu_init;       /* initial barrier parameter, <= 0: 1e-3 (Ipopt warm_start_mult_bound_push) */
   double bound_push;    /* <= 0: 1e-3 (Ipopt warm_start_bound_push) */
   int32_t device;       /* CUDA device ordinal, -1: current device */
   int32_t threads;      /* threads per CTA, <= 0: default */

@@ -296,7 +296,7 @@ void eval_full(const Prob& P, const double* x, const double* p, const double* la
 struct Opts {
   double tol = 1e-8;
   int max_iter = 500;
-  double mu_init = 0.1;
+  double mu_init = 1e-3;      // level of Ipopt's warm_start_mult_bound_push (see bmpc_host.h make_config)
   double bound_push = 1e-3;   // Ipopt warm_start_bound_push / warm_start_slack_bound_push
   double kappa_eps = 10, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100;
   double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta_sw = 1.0;

@@ -63,7 +63,7 @@ def derivs(x, p, lam, N=10, S=4, dt=0.1):
     return grad, jac, hess
 
 
-def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=0.1, bound_push=1e-3, verbose=0):
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=1e-3, bound_push=1e-3, verbose=0):
     n, m, _ = dims(N, S)
     x0 = np.ascontiguousarray(x0, float)
     p = np.ascontiguousarray(p, float)

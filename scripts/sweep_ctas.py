@@ -1,0 +1,28 @@
+"""Device throughput of k_solve<128,3> with 1, 2, 3 resident CTAs per SM (development aid: how well do CTAs overlap?)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from boundmpc_b200.ocp import default_solver
+from boundmpc_b200 import batches
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+base = default_solver()
+x0, p = batches.make_batch(base, ("exp1", "exp2"), 0, B, bound_scale=True)
+xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
+for threads, ctas in [(128, 1), (128, 2), (128, 3)]:
+    os.environ["BMPC_THREADS"], os.environ["BMPC_CTAS_PER_SM"] = str(threads), str(ctas)
+    s = default_solver()
+    out = s.solve_batch(xd, pd); torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); s.solve_batch(xd, pd, out); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(json.dumps({"threads": threads, "ctas_per_sm": ctas, "B": B, "ms": best, "solves_per_s": B / best * 1e3,
+                      "shape": s.launch_shape(), "ok": int((out["status"] == 0).sum())}), flush=True)
+it = out["iters"].cpu().numpy(); st = out["status"].cpu().numpy()
+os.makedirs("gpurun_out", exist_ok=True)
+np.savez("gpurun_out/iters_status.npz", iters=it, status=st)
+print("iters mean %.2f p50 %d p90 %d p99 %d max %d; status counts %s; iters of failures %s" % (
+    it.mean(), np.percentile(it, 50), np.percentile(it, 90), np.percentile(it, 99), it.max(),
+    dict(zip(*np.unique(st, return_counts=True))), it[st != 0].tolist()))

