@@ -18,6 +18,7 @@
 #define BMPC_HD inline
 #define BMPC_SYNC() ((void)0)
 #define BMPC_LDG(ptr) (*(ptr))
+#define BMPC_LDCG(ptr) (*(ptr))
 #else
 #define BMPC_DEV __device__ __forceinline__
 // large phase bodies exist once in the kernel image (the interior-point loop has to stay resident in
@@ -26,6 +27,7 @@
 #define BMPC_HD __host__ __device__ inline
 #define BMPC_SYNC() __syncthreads()
 #define BMPC_LDG(ptr) __ldg(ptr)
+#define BMPC_LDCG(ptr) __ldcg(ptr)   // data another SM wrote during this launch: read at L2
 #endif
 
 // optional per-phase cycle accounting of thread 0 (development build, -DBMPC_TIMING)
@@ -230,7 +232,7 @@ struct Config {
   double dt;
   double lb[NX], ub[NX];   // per-stage variable bounds (+-inf where free)
   // interior-point options
-  double tol;
+  double tol, diverge_tol;
   int max_iter;
   double mu_init, bound_push;
   double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
@@ -355,6 +357,6 @@ template <int K>
 BMPC_DEV void block_reduce(const Ctx cx, double (&v)[K], const int (&op)[K]) { block_reduce_n(cx, v, op, K); }
 
 // status codes returned per instance
-enum { ST_SUCCESS = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_NUMERIC = 4 };
+enum { ST_SUCCESS = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_NUMERIC = 4, ST_DIVERGING = 5 };
 
 }  // namespace bmpc

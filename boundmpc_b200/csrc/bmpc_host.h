@@ -23,6 +23,11 @@ inline int make_config(const bmpc_config& in, Config& C) {
   C.lb[oPHI] = 0.0;
   C.tol = in.tol > 0 ? in.tol : 1e-9;
   C.max_iter = in.max_iter > 0 ? in.max_iter : 500;
+  // Without a restoration phase a locally infeasible instance (a start outside the error bounds that the jerk limit
+  // cannot bring back within the first nodes) drifts for 100+ iterations with growing multipliers before the line
+  // search gives up; the iteration stops when the dual infeasibility passes this level (converging instances of the
+  // bench workload stay below 3e5).
+  C.diverge_tol = 1e7;
   // initial barrier parameter / initial bound multipliers z = mu / slack.  The reference runs Ipopt's adaptive strategy
   // with warm_start_init_point (BoundMPC.py:120-141), which starts from the complementarity of the pushed start
   // (warm_start_mult_bound_push = 1e-3) instead of the monotone mode's mu_init = 0.1; 1e-3 reproduces that level

@@ -19,6 +19,11 @@
 
 namespace bmpc {
 
+#ifdef BMPC_TRACE
+__device__ double g_itlog[12 * 500];
+__device__ int g_itlog_on;
+#endif
+
 struct InstanceIO {
   const double* x0;   // [n]
   const double* p;    // [np]
@@ -34,9 +39,42 @@ struct InstanceIO {
 
 BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 
-BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io) {
+// Two-pass scheduling of a batch (k_solve): pass A runs the first SLICE_ITERS iterations of every instance and
+// parks the iterate in global memory; pass B resumes the parked instances, those whose optimality error has grown
+// over the slice ("hard": the few instances that go on for 50-150 iterations) first.  Starting the long solves
+// early keeps them out of the tail of the launch (longest-processing-time-first; the work queue alone leaves
+// 30 % of the GPU idle behind them on the bench workload).  Results do not depend on where an instance is parked.
+constexpr int SLICE_ITERS = 6;
+constexpr int SAVE_FILT = 128, SAVE_SCAL = 16;
+BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
+enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
+enum { DONE = 0, PARKED = 1, PARKED_HARD = 2 };                  // its return value
+
+BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io, int mode = RUN_FULL,
+                            double* save = nullptr) {
   const int N = C.N, n = C.n, ne = NE * N, nd = ND * N;
   const double* p = io.p;
+  double mu = C.mu_init;
+  double theta_max = 0.0, theta_min = 0.0, delta_w_last = 0.0, kkt_final = 0.0, fval = 0.0, e0_first = 0.0;
+  bool have_theta0 = false;
+  int status = ST_MAXITER, it = 0, ls_fail = 0;
+  if (mode == RUN_RESUME) {
+    // ---- restore the parked iterate
+    build_wp0(cx, C, p, W.wp0);
+    const double* q = save;
+    PAR_FOR(i, n) { W.x[i] = BMPC_LDCG(q + i); W.zL[i] = BMPC_LDCG(q + n + i); W.zU[i] = BMPC_LDCG(q + 2 * n + i); }
+    q += 3 * n;
+    PAR_FOR(i, ne) W.y[i] = BMPC_LDCG(q + i);
+    q += ne;
+    PAR_FOR(i, nd) { W.s[i] = BMPC_LDCG(q + i); W.zs[i] = BMPC_LDCG(q + nd + i); }
+    q += 2 * nd;
+    PAR_FOR(i, SAVE_FILT) S.filt[i] = BMPC_LDCG(q + i);
+    q += SAVE_FILT;
+    mu = BMPC_LDCG(q + 0); theta_max = BMPC_LDCG(q + 1); theta_min = BMPC_LDCG(q + 2); delta_w_last = BMPC_LDCG(q + 3); e0_first = BMPC_LDCG(q + 4);
+    have_theta0 = BMPC_LDCG(q + 5) != 0.0; it = (int)BMPC_LDCG(q + 6); ls_fail = (int)BMPC_LDCG(q + 7);
+    if (cx.tid == 0) S.flag[1] = (int)BMPC_LDCG(q + 8);
+    BMPC_SYNC();
+  } else {
   // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)
   build_wp0(cx, C, p, W.wp0);
   PAR_FOR(i, n) {
@@ -54,7 +92,6 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
   }
   PAR_FOR(i, ne) W.y[i] = 0.0;
   BMPC_SYNC();
-  double mu = C.mu_init;
   eval_values(cx, C, W, p, W.x, W.c, W.d);
   PAR_FOR(i, nd) { const double sv = fmax(-W.d[i], C.bound_push); W.s[i] = sv; W.zs[i] = mu / sv; }
   PAR_FOR(i, n) {
@@ -66,15 +103,31 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
   if (cx.tid == 0) S.flag[1] = 0;   // filter size
   BMPC_SYNC();
   BMPC_TMARK(22);
+  }
 
   int nbnd = 0;
   for (int i = 0; i < NX; i++) nbnd += (C.lb[i] > -1e300) + (C.ub[i] < 1e300);
   const double nzcnt = (double)N * (ND + nbnd);
-  double theta_max = 0.0, theta_min = 0.0, delta_w_last = 0.0, kkt_final = 0.0, fval = 0.0;
-  bool have_theta0 = false;
-  int status = ST_MAXITER, it = 0, ls_fail = 0;
 
   for (;; it++) {
+    if (mode == RUN_SLICE && it == SLICE_ITERS) {
+      // ---- park the iterate (every quantity the loop carries; everything else is recomputed by eval_full)
+      double* q = save;
+      PAR_FOR(i, n) { q[i] = W.x[i]; q[n + i] = W.zL[i]; q[2 * n + i] = W.zU[i]; }
+      q += 3 * n;
+      PAR_FOR(i, ne) q[i] = W.y[i];
+      q += ne;
+      PAR_FOR(i, nd) { q[i] = W.s[i]; q[nd + i] = W.zs[i]; }
+      q += 2 * nd;
+      PAR_FOR(i, SAVE_FILT) q[i] = S.filt[i];
+      q += SAVE_FILT;
+      if (cx.tid == 0) {
+        q[0] = mu; q[1] = theta_max; q[2] = theta_min; q[3] = delta_w_last; q[4] = e0_first;
+        q[5] = have_theta0 ? 1.0 : 0.0; q[6] = (double)it; q[7] = (double)ls_fail; q[8] = (double)S.flag[1];
+      }
+      BMPC_SYNC();
+      return kkt_final > e0_first ? PARKED_HARD : PARKED;
+    }
     eval_full(cx, C, W, p, W.x);
     // ---- optimality error (Ipopt's E_mu), constraint violation theta
     double rv[8] = {0, 0, 0, 0, 1e300, 0, 0, 0};   // dinf, pinf, ysum, zsum, szmin, szmax, theta, f
@@ -113,9 +166,11 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
     const double sc = fmax(C.s_max, zsum / nzcnt) / C.s_max;
     const double e0 = fmax(dinf / sd, fmax(pinf, fmax(szmax, 0.0) / sc));
     kkt_final = e0;
+    if (it == 0) e0_first = e0;
     if (!(e0 == e0) || !(th_cur < 1e300)) { status = ST_NUMERIC; break; }
     if (e0 <= C.tol) { status = ST_SUCCESS; break; }
     if (it >= C.max_iter) { status = ST_MAXITER; break; }
+    if (dinf > C.diverge_tol) { status = ST_DIVERGING; break; }
     // ---- barrier parameter: monotone Fiacco-McCormick (Waechter & Biegler 2006, eq. (7))
     bool mu_changed = false;
     for (;;) {
@@ -221,10 +276,15 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
         if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }
       if (!filt_ok) continue;
       const bool sw = dphi < 0 && alpha * bmpc_pow(-dphi, C.s_phi) > (th_cur > 0 ? bmpc_pow(th_cur, C.s_theta) : 0.0);
+      // comparisons with Ipopt's round-off allowance (Compare_le: lhs - rhs <= 10 eps |reference value|): close to the
+      // solution the decrease conditions are decided by rounding noise, and a strict test sends the iteration into
+      // dozens of useless backtracking steps (seen on the device: 87 instead of 11 iterations on a bench instance)
+      const double ro = 10 * 2.220446049250313e-16;
       if (th_cur <= theta_min && sw) {
-        if (ph_t <= phi_cur + C.eta_phi * alpha * dphi) { accepted = true; ftype = true; break; }
+        if (ph_t - phi_cur - C.eta_phi * alpha * dphi <= ro * fabs(phi_cur)) { accepted = true; ftype = true; break; }
       } else {
-        if (th_t <= (1 - C.gamma_theta) * th_cur || ph_t <= phi_cur - C.gamma_phi * th_cur) { accepted = true; ftype = false; break; }
+        if (th_t - (1 - C.gamma_theta) * th_cur <= ro * fabs(th_cur) ||
+            ph_t - phi_cur + C.gamma_phi * th_cur <= ro * fabs(phi_cur)) { accepted = true; ftype = false; break; }
       }
     }
     if (!accepted) {
@@ -262,6 +322,13 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
     PAR_FOR(i, ne) W.y[i] += alpha * (W.ynew[i] - W.y[i]);
     BMPC_SYNC();
     BMPC_TMARK(21);
+#ifdef BMPC_TRACE
+    if (cx.tid == 0 && it < 500 && g_itlog_on) {   // development build: iteration log of a single-instance launch
+      double* L = g_itlog + 12 * it;
+      L[0] = e0; L[1] = dinf; L[2] = pinf; L[3] = mu; L[4] = alpha; L[5] = apr; L[6] = adu; L[7] = dwreg; L[8] = th_cur; L[9] = phi_cur;
+      L[10] = dphi; L[11] = (accepted ? 1.0 : 0.0) + (ftype ? 2.0 : 0.0) + 4.0 * ls_fail;
+    }
+#endif
   }
 
   // ---- report in the reference's conventions: x, g, lam_g, lam_x (CasADi: L = f + lam_g.g + lam_x.x)
@@ -291,6 +358,7 @@ BMPC_DEV void solve_instance(const Ctx cx, const Config& C, const Work& W, Smem&
   if (cx.tid == 0) { *io.f = fval; *io.kkt = kkt_final; *io.iters = it; *io.status = status; }
   BMPC_SYNC();
   BMPC_TMARK(23);
+  return DONE;
 }
 
 }  // namespace bmpc

@@ -28,6 +28,18 @@ struct BatchIO {
   int32_t *iters, *status;
 };
 
+#ifdef BMPC_TRACE
+// development build: per-instance time stamps (globaltimer, ns) of the scheduler: [b][0..1] first run, [b][2..3] resumed run
+__device__ unsigned long long g_trace[65536 * 4];
+extern "C" int bmpc_trace(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : -2;
+}
+extern "C" int bmpc_itlog(double* out, int enable) {
+  if (enable >= 0) return cudaMemcpyToSymbol(bmpc::g_itlog_on, &enable, sizeof(int)) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(out, bmpc::g_itlog, sizeof(double) * 12 * 500) == cudaSuccess ? 0 : -2;
+}
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #ifdef BMPC_TIMING
 __device__ unsigned long long g_phase_cycles[64];
 extern "C" int bmpc_phase_cycles(unsigned long long* out, int reset) {
@@ -37,9 +49,50 @@ extern "C" int bmpc_phase_cycles(unsigned long long* out, int reset) {
 }
 #endif
 
+// Work queue of a launch (first 256 bytes of the workspace).  Single pass (batch <= grid): `next` hands out instances.
+// Two passes (see SLICE_ITERS in bmpc_ipm.cuh): `next` hands out the pass-A slices; a CTA that has parked an instance
+// appends it to the hard or the normal list (tail, then the slot, then `parked`); once pass A is handed out, CTAs pop
+// the hard list first, then the normal list, and leave when every slice has been parked or finished and both lists
+// are drained.
+struct Sched { unsigned int next, sliced, tail_h, head_h, tail_n, head_n; };
+struct SchedMem { Sched* sc; int* list_h; int* list_n; double* save; size_t save_stride; int two_pass; };
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+
+// thread 0: next piece of work of this CTA; returns the instance (or -1: nothing left) and the mode
+__device__ int sched_next(const SchedMem& M, int batch, int* mode) {
+  Sched* sc = M.sc;
+  const unsigned int t = atomicAdd(&sc->next, 1u);
+  if (t < (unsigned int)batch) { *mode = M.two_pass ? RUN_SLICE : RUN_FULL; return (int)t; }
+  if (!M.two_pass) return -1;
+  *mode = RUN_RESUME;
+  for (;;) {
+    for (int which = 0; which < 2; which++) {
+      unsigned int* head = which ? &sc->head_n : &sc->head_h;
+      const unsigned int* tail = which ? &sc->tail_n : &sc->tail_h;
+      const int* list = which ? M.list_n : M.list_h;
+      for (;;) {
+        const unsigned int h = ld_volatile_u32(head);
+        if (h >= ld_volatile_u32(tail)) break;
+        if (atomicCAS(head, h, h + 1) != h) continue;
+        int b;
+        while ((b = *(const volatile int*)(list + h)) < 0) __nanosleep(100);   // (slot reserved, index not yet written)
+        __threadfence();
+        return b;
+      }
+    }
+    if (ld_volatile_u32(&sc->sliced) >= (unsigned int)batch) {
+      __threadfence();
+      if (ld_volatile_u32(&sc->head_h) >= ld_volatile_u32(&sc->tail_h) && ld_volatile_u32(&sc->head_n) >= ld_volatile_u32(&sc->tail_n)) return -1;
+    } else {
+      __nanosleep(1000);
+    }
+  }
+}
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C0, int batch, BatchIO io, double* ws,
-                                                         size_t ws_stride, unsigned int* counter) {
+                                                         size_t ws_stride, SchedMem M) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 #ifdef BMPC_TIMING
@@ -60,14 +113,32 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
   build_tables(cx, C, S);
   phase_kin_jacobian_init(cx, C, W);
   for (;;) {
-    if (threadIdx.x == 0) S.flag[2] = (int)atomicAdd(counter, 1u);
+    if (threadIdx.x == 0) { int mode = RUN_FULL; S.flag[2] = sched_next(M, batch, &mode); S.flag[0] = mode; }
     __syncthreads();
-    const int b = S.flag[2];
+    const int b = S.flag[2], mode = S.flag[0];
     __syncthreads();
-    if (b >= batch) break;
+    if (b < 0) break;
     InstanceIO ii{io.x0 + (size_t)b * C.n, io.p + (size_t)b * C.np, io.x + (size_t)b * C.n, io.g + (size_t)b * C.m,
                   io.lam_g + (size_t)b * C.m, io.lam_x + (size_t)b * C.n, io.f + b, io.kkt + b, io.iters + b, io.status + b};
-    solve_instance(cx, C, W, S, ii);
+#ifdef BMPC_TRACE
+    if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 2 : 0)] = gtime();
+#endif
+    const int rc = solve_instance(cx, C, W, S, ii, mode, M.save ? M.save + (size_t)b * M.save_stride : nullptr);
+#ifdef BMPC_TRACE
+    if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 3 : 1)] = gtime() | (rc == PARKED_HARD ? 1ull : 0ull);
+#endif
+    if (mode == RUN_SLICE) {
+      __threadfence();          // the parked iterate, written by all threads, before the list entry that publishes it
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (rc != DONE) {
+          const unsigned int slot = atomicAdd(rc == PARKED_HARD ? &M.sc->tail_h : &M.sc->tail_n, 1u);
+          *(volatile int*)((rc == PARKED_HARD ? M.list_h : M.list_n) + slot) = b;
+          __threadfence();
+        }
+        atomicAdd(&M.sc->sliced, 1u);
+      }
+    }
   }
 #ifdef BMPC_TIMING
   if (threadIdx.x < 62) atomicAdd(&g_phase_cycles[threadIdx.x], (unsigned long long)S.tm[threadIdx.x]);
@@ -75,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 }
 
 // launch variants: (threads per CTA, resident CTAs per SM the register budget is compiled for)
-typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, unsigned int*);
+typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, SchedMem);
 struct SolveVariant { int threads, minb; solve_fn fn; };
 static const SolveVariant kVariants[] = {
 #ifdef BMPC_TIMING
@@ -260,7 +331,9 @@ int bmpc_bounds(const bmpc_handle* h, double* lbx, double* ubx, double* lbg, dou
 
 int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes) {
   if (!h || !bytes || batch < 0) return fail(BMPC_E_INVALID, "bmpc_workspace_bytes: invalid argument");
-  *bytes = 256 + (size_t)grid_for(h, batch > 0 ? batch : 1) * h->ws_stride * sizeof(double);
+  const int b = batch > 0 ? batch : 1, grid = grid_for(h, b);
+  *bytes = 256 + (size_t)grid * h->ws_stride * sizeof(double);
+  if (b > grid) *bytes += align_up((size_t)2 * b * sizeof(int), 256) + (size_t)b * align_up(save_doubles(h->C.N), 32) * sizeof(double);   // two-pass scheduling
   return BMPC_OK;
 }
 
@@ -312,12 +385,23 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
   if (batch == 0) return BMPC_OK;
   CU(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  unsigned int* counter = (unsigned int*)workspace;
-  double* ws = (double*)((char*)workspace + 256);
-  CU(cudaMemsetAsync(counter, 0, 256, st));
-  BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status};
   const int grid = grid_for(h, batch);
-  kVariants[h->variant].fn<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, counter);
+  // workspace: [queue 256 B][per-CTA slices][parked lists 2 x batch int][parked iterates batch x save_stride]
+  char* wsb = (char*)workspace;
+  double* ws = (double*)(wsb + 256);
+  SchedMem M{(Sched*)wsb, nullptr, nullptr, nullptr, 0, 0};
+  CU(cudaMemsetAsync(wsb, 0, 256, st));
+  if (batch > grid && !getenv("BMPC_SINGLE_PASS")) {
+    const size_t o_list = 256 + (size_t)grid * h->ws_stride * sizeof(double), list_bytes = align_up((size_t)2 * batch * sizeof(int), 256);
+    M.list_h = (int*)(wsb + o_list);
+    M.list_n = M.list_h + batch;
+    M.save = (double*)(wsb + o_list + list_bytes);
+    M.save_stride = align_up(save_doubles(h->C.N), 32);
+    M.two_pass = 1;
+    CU(cudaMemsetAsync(M.list_h, 0xFF, (size_t)2 * batch * sizeof(int), st));
+  }
+  BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status};
+  kVariants[h->variant].fn<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, M);
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

@@ -13,7 +13,7 @@ import numpy as np
 from . import _cabi
 
 RETURN_STATUS = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Failed",
-                 3: "Error_In_Step_Computation", 4: "Invalid_Number_Detected"}
+                 3: "Error_In_Step_Computation", 4: "Invalid_Number_Detected", 5: "Infeasible_Problem_Detected"}
 
 
 def _g_names(N):

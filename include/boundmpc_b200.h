@@ -52,6 +52,7 @@ typedef struct bmpc_config {
 #define BMPC_STATUS_LINESEARCH 2
 #define BMPC_STATUS_REGULARIZATION 3
 #define BMPC_STATUS_NUMERIC 4
+#define BMPC_STATUS_DIVERGING 5   /* multipliers diverge (dual infeasibility > 1e7): locally infeasible instance */
 
 /* error codes */
 #define BMPC_OK 0

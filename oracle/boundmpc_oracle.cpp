@@ -301,6 +301,7 @@ struct Opts {
   double kappa_eps = 10, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100;
   double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta_sw = 1.0;
   int verbose = 0;
+  double diverge_tol = 1e7;   // dual infeasibility beyond which the multipliers are taken to diverge (locally infeasible instance)
 };
 
 struct Ipm {
@@ -592,7 +593,7 @@ struct Ipm {
     filter.clear();
     double theta0 = -1, theta_max = 0, theta_min = 0;
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
-    int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure
+    int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
     for (;; it++) {
       pack_lam();
@@ -603,6 +604,7 @@ struct Ipm {
       kkt_final = e0;
       if (e0 <= o.tol) { status = 0; break; }
       if (it >= o.max_iter) { status = 1; break; }
+      if (parts[0] > o.diverge_tol) { status = 5; break; }
       // barrier parameter (monotone Fiacco-McCormick, Ipopt eq. (7))
       bool mu_changed = false;
       while (mu > o.tol / 10 && kkt_error(mu) <= o.kappa_eps * mu) {
@@ -684,10 +686,15 @@ struct Ipm {
           if (!(th_t < fe.first || ph_t < fe.second)) { filt_ok = false; break; }
         if (!filt_ok) continue;
         bool sw = dphi < 0 && alpha * std::pow(-dphi, o.s_phi) > o.delta_sw * std::pow(th_cur, o.s_theta);
+        // comparisons with Ipopt's round-off allowance (Compare_le: lhs - rhs <= 10 eps |reference value|): close to the
+        // solution the decrease conditions are decided by rounding noise and a strict test sends the iteration
+        // into dozens of useless backtracking steps
+        const double ro = 10 * 2.220446049250313e-16;
         if (th_cur <= theta_min && sw) {
-          if (ph_t <= phi_cur + o.eta_phi * alpha * dphi) { accepted = true; ftype = true; break; }
+          if (ph_t - phi_cur - o.eta_phi * alpha * dphi <= ro * std::fabs(phi_cur)) { accepted = true; ftype = true; break; }
         } else {
-          if (th_t <= (1 - o.gamma_theta) * th_cur || ph_t <= phi_cur - o.gamma_phi * th_cur) { accepted = true; ftype = false; break; }
+          if (th_t - (1 - o.gamma_theta) * th_cur <= ro * std::fabs(th_cur) ||
+              ph_t - phi_cur + o.gamma_phi * th_cur <= ro * std::fabs(phi_cur)) { accepted = true; ftype = false; break; }
         }
       }
       if (!accepted) {

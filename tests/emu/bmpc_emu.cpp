@@ -34,6 +34,36 @@ int emu_solve(const bmpc_config* cfg, int batch, const double* x0, const double*
   return 0;
 }
 
+// the two-pass path of k_solve: every instance is parked after its first slice (pass A), then all are resumed in
+// reverse order (pass B) on the same scratch; hard[b] receives the "hard" flag of the parking decision (-1: finished in pass A)
+int emu_solve_sliced(const bmpc_config* cfg, int batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+                     double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt, int32_t* hard) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  std::vector<double> ws(work_doubles(C.N));
+  const size_t stride = save_doubles(C.N);
+  std::vector<double> save(stride * (size_t)batch);
+  Smem* S = new Smem;
+  Work W;
+  work_carve(W, ws.data(), C.N);
+  work_attach_smem(W, *S, C.N);
+  Ctx cx{0, 1, S->red};
+  build_tables(cx, C, *S);
+  phase_kin_jacobian_init(cx, C, W);
+  auto make_io = [&](int b) {
+    return InstanceIO{x0 + (size_t)b * C.n, p + (size_t)b * C.np, x + (size_t)b * C.n, g + (size_t)b * C.m,
+                      lam_g + (size_t)b * C.m, lam_x + (size_t)b * C.n, f + b, kkt + b, iters + b, status + b};
+  };
+  for (int b = 0; b < batch; b++) {
+    const int rc = solve_instance(cx, C, W, *S, make_io(b), RUN_SLICE, save.data() + stride * b);
+    hard[b] = rc == DONE ? -1 : (rc == PARKED_HARD ? 1 : 0);
+  }
+  for (int b = batch - 1; b >= 0; b--)
+    if (hard[b] >= 0) solve_instance(cx, C, W, *S, make_io(b), RUN_RESUME, save.data() + stride * b);
+  delete S;
+  return 0;
+}
+
 int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p, const double* lam, double* f, double* g,
              double* d, double* grad, double* jac, double* hess) {
   Config C;

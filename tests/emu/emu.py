@@ -52,7 +52,8 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
-def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-9, max_iter=500, sliced=False):
+    """sliced=True: the park / resume path of the two-pass scheduling (adds the key 'hard')."""
     x0 = np.ascontiguousarray(np.atleast_2d(x0), float)
     p = np.ascontiguousarray(np.atleast_2d(p), float)
     B, n = x0.shape
@@ -61,8 +62,15 @@ def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
     x, g, lg, lx = np.empty((B, n)), np.empty((B, m)), np.empty((B, m)), np.empty((B, n))
     f, kkt = np.empty(B), np.empty(B)
     it, st = np.empty(B, np.int32), np.empty(B, np.int32)
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    if sliced:
+        hard = np.empty(B, np.int32)
+        rc = lib().emu_solve_sliced(ctypes.byref(cfg), B, _p(x0), _p(p), _p(x), _p(g), _p(lg), _p(lx), _p(f),
+                                    it.ctypes.data_as(i32p), st.ctypes.data_as(i32p), _p(kkt), hard.ctypes.data_as(i32p))
+        assert rc == 0
+        return dict(x=x, g=g, lam_g=lg, lam_x=lx, f=f, iters=it, status=st, kkt=kkt, hard=hard)
     rc = lib().emu_solve(ctypes.byref(cfg), B, _p(x0), _p(p), _p(x), _p(g), _p(lg), _p(lx), _p(f),
-                         it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _p(kkt))
+                         it.ctypes.data_as(i32p), st.ctypes.data_as(i32p), _p(kkt))
     assert rc == 0
     return dict(x=x, g=g, lam_g=lg, lam_x=lx, f=f, iters=it, status=st, kkt=kkt)
 

@@ -50,3 +50,16 @@ def test_same_iterates_as_oracle():
         re = emu.solve(S["x0"][i], S["p"][i], tol=1e-9)
         assert ro["iters"] == re["iters"][0]
         assert np.abs(ro["x"] - re["x"][0]).max() < 1e-8
+
+
+def test_park_and_resume_is_bitwise_neutral():
+    """Two-pass scheduling of k_solve: parking an instance after its first slice and resuming it later (other
+    instances in between, same scratch) must not change a single bit of the result."""
+    S1, S2 = load("seq_exp1.npz"), load("seq_exp2.npz")
+    x0 = np.concatenate([S1["x0"][:6], S2["x0"][:6]])
+    p = np.concatenate([S1["p"][:6], S2["p"][:6]])
+    a = emu.solve(x0, p)
+    b = emu.solve(x0, p, sliced=True)
+    assert (b["hard"] >= 0).sum() >= 10         # (an instance that converges within the first slice is never parked)
+    for k in ("x", "g", "lam_g", "lam_x", "f", "kkt", "iters", "status"):
+        assert np.array_equal(a[k], b[k]), k
