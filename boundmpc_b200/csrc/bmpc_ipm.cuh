@@ -248,6 +248,11 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     double alpha = apr;
     bool accepted = false, ftype = false;
     const int nfilt = S.flag[1];
+    // flat merit functions: with the constraint violation at rounding level and no measurable predicted change of the
+    // barrier objective the decrease tests below only see noise (on the device they cut the step to ~1e-9 for dozens of
+    // iterations while the dual infeasibility stays above tol); Newton's full step is taken instead, as Ipopt does for
+    // its "tiny steps"
+    const bool flat = th_cur <= 1e-10 && fabs(dphi) <= 1e-10 * fmax(1.0, fabs(phi_cur));
     for (int ls = 0; ls < 40; ls++, alpha *= 0.5) {
       PAR_FOR(i, n) W.xt[i] = W.x[i] + alpha * W.dx[i];
       PAR_FOR(i, nd) W.st[i] = W.s[i] + alpha * W.ds[i];
@@ -271,6 +276,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       BMPC_TMARK(20);
       const double th_t = tv2[0], ph_t = tv2[1];
       if (!(th_t == th_t) || !(ph_t == ph_t) || !(th_t < 1e300) || !(fabs(ph_t) < 1e300) || th_t > theta_max) continue;
+      if (flat) { accepted = true; ftype = true; break; }
       bool filt_ok = true;
       for (int q = 0; q < nfilt; q++)
         if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }

@@ -673,6 +673,11 @@ struct Ipm {
       double alpha = apr;
       bool accepted = false, ftype = false;
       double th_t = 0, ph_t = 0;
+      // flat merit functions: with the constraint violation at rounding level and no measurable predicted change of
+      // the barrier objective the decrease tests below only see noise (they then cut the step to ~1e-9 for dozens
+      // of iterations while the dual infeasibility stays above tol); Newton's full step is taken instead, as Ipopt
+      // does for its "tiny steps"
+      const bool flat = th_cur <= 1e-10 && std::fabs(dphi) <= 1e-10 * std::max(1.0, std::fabs(phi_cur));
       for (int ls = 0; ls < 40; ls++, alpha *= 0.5) {
         for (int i = 0; i < n; i++) xt[i] = x[i] + alpha * dx[i];
         for (int i = 0; i < ni; i++) st[i] = s[i] + alpha * ds[i];
@@ -681,6 +686,7 @@ struct Ipm {
         th_t = theta(gt.data(), dt_.data(), st);
         ph_t = barrier_phi(ft, xt, st);
         if (!std::isfinite(th_t) || !std::isfinite(ph_t) || th_t > theta_max) continue;
+        if (flat) { accepted = true; ftype = true; break; }
         bool filt_ok = true;
         for (auto& fe : filter)
           if (!(th_t < fe.first || ph_t < fe.second)) { filt_ok = false; break; }
