@@ -293,6 +293,46 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- batched parameter builder (the pre-solve half of BoundMPC.step), rank 0
+    from boundmpc_b200 import batches
+    nb = 512
+    t0 = time.perf_counter()
+    D = batches.make_builder_batch(solver, ("exp1", "exp2"), 0, nb, bound_scale=True)
+    t_mirror = time.perf_counter() - t0          # host mirror: controller restore + prepare() per instance (Python)
+    rep = (per_gpu + nb - 1) // nb
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * rep)[:per_gpu])
+    tb = {k: torch.from_numpy(tile(D[k])).to(dev) for k in ("path_id", "sector", "state", "prev")}
+    tb["tables"] = torch.from_numpy(D["tables"]).to(dev)
+    sec0 = tb["sector"].clone()
+    bo = solver.prepare_batch(tb["tables"], tb["path_id"], tb["sector"], tb["state"], tb["prev"])
+    torch.cuda.synchronize()
+    perr = float((np.abs(bo["p"][:nb].cpu().numpy() - D["p"]) / np.maximum(1.0, np.abs(D["p"]))).max())
+    x0_same = bool(np.array_equal(bo["x0"][:nb].cpu().numpy(), D["x0"]))
+    b_ms = []
+    for k in range(args.warmup + args.steps):
+        tb["sector"].copy_(sec0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.prepare_batch(tb["tables"], tb["path_id"], tb["sector"], tb["state"], tb["prev"], bo)
+        b.record()
+        torch.cuda.synchronize()
+        if k >= args.warmup:
+            b_ms.append(a.elapsed_time(b))
+    b_ms = float(np.mean(b_ms))
+    bytes_inst = 76 * 8 + 8 + n * 8 + n * 8 + npar * 8          # state, path id + sector, prev_x in; x0, p out
+    hs = {k: tile(D[k]) for k in ("path_id", "sector", "state", "prev")}
+    solver.prepare_batch(D["tables"], hs["path_id"], hs["sector"], hs["state"], hs["prev"])
+    t0 = time.perf_counter()
+    solver.prepare_batch(D["tables"], hs["path_id"], hs["sector"], hs["state"], hs["prev"])
+    b_e2e = time.perf_counter() - t0
+    builder = {"kernel": "k_prepare", "instances": per_gpu, "ms": b_ms, "instances_per_s": per_gpu / (b_ms * 1e-3),
+               "bytes_per_instance": bytes_inst,
+               "hbm": {"achieved": per_gpu * bytes_inst / (b_ms * 1e-3) / 1e9, "unit": "GB/s"},
+               "e2e_instances_per_s": per_gpu / b_e2e,
+               "parity": {"p_rel_err_vs_host_mirror": perr, "x0_bitwise_equal": x0_same, "checked": nb},
+               "cpu_mirror": {"instances_per_s": nb / t_mirror, "what": "boundmpc_b200.bound_mpc.BoundMPC.prepare (numpy mirror of "
+                              "BoundMPC.py:310-443) incl. controller-state restore, 1 thread"}}
+
     sum_iters = float(cnt[1].item())
     ach = float(iters.sum()) * F_ITER[10] / (k_ms * 1e-3)          # rank 0's kernel: flop / s
     hbm = per_gpu * IO_BYTES[10] / (k_ms * 1e-3) / 1e9
@@ -302,6 +342,7 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    builder["hbm"].update(peak=hbm_peak, frac=builder["hbm"]["achieved"] / hbm_peak)
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_dram_bytes_per_launch")
@@ -326,6 +367,7 @@ def main():
                        "iters_max_rank0": int(iters.max()), "kkt_max_rank0": float(kkt[status == 0].max()) if ok else None,
                        "perturbation_scale_hist_rank0": {str(v): int((scale == v).sum()) for v in np.unique(scale)},
                        "input_generation_s": t_gen},
+            "builder": builder,
             "latency_b1_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "max": float(max(lat)),
                               "what": "one instance through bmpc_solve_batch_host incl. H2D/D2H, wall clock"}}
     if world == 1 and not args.no_cpu_baseline:

@@ -114,6 +114,60 @@ def perturbed_instance(mpc, snaps, x_phi_d, i, bound_scale=False, scale=1.0):
     return w0, p, _rollout(rm, w0, p, mpc.dt, CHECK_STAGES)
 
 
+def builder_instance(mpc, snaps, x_phi_d, i, bound_scale=False, scale=1.0):
+    """Instance i as input of the CUDA parameter builder (`BatchSolver.prepare_batch`): state vector, window position and
+    previous solution, next to the (x0, p) the host mirror's `prepare()` builds from the same controller state."""
+    rng = np.random.default_rng(SEED0 + i)
+    snap, st = snaps[i % len(snaps)]
+    _restore(mpc, snap)
+    nq, ndq, nddq = rng.normal(0.0, SIGMA_Q, 7), rng.normal(0.0, SIGMA_DQ, 7), rng.normal(0.0, SIGMA_DDQ, 7)
+    q = np.clip(st['q'] + scale * nq, Q_LIM_LOWER + 0.05, Q_LIM_UPPER - 0.05)
+    dq = np.clip(st['dq'] + scale * ndq, DQ_LIM_LOWER + 0.05, DQ_LIM_UPPER - 0.05)
+    ddq = st['ddq'] + scale * nddq
+    f = rng.uniform(1.0, 1.25, 4) if bound_scale else np.ones(4)
+    rm = mpc.robot_model
+    p0 = rm.fk(q)
+    v0 = rm.jacobian_fk(q) @ dq
+    state, sector, prev = mpc.builder_state(q, dq, ddq, p0, v0, x_phi_d, st['jerk'], bound_scale=f)
+    if bound_scale:
+        rp = mpc.ref_path
+        rp.e_p_min = [v * f[0] for v in rp.e_p_min]
+        rp.e_r_min = [v * f[1] for v in rp.e_r_min]
+        rp.e_p_max = [v * f[2] for v in rp.e_p_max]
+        rp.e_r_max = [v * f[3] for v in rp.e_r_max]
+    w0, p, _ = mpc.prepare(q, dq, ddq, p0, v0, x_phi_d, st['jerk'])
+    return state, sector, prev, w0, p, int(mpc.ref_path.sector)
+
+
+def make_builder_batch(solver, scenario_names, first, count, n=10, bound_scale=False):
+    """Inputs of the parameter builder for instances `first .. first+count-1` plus the host mirror's outputs.
+    Returns dict(tables [P, J, 38], path_id, sector, state, prev, x0, p, sector_out)."""
+    names = sorted(set(scenario_names))
+    seqs, tabs = {}, []
+    for name in names:
+        scn = scenarios.experiment1(n=n) if name == 'exp1' else scenarios.experiment2(n=n)
+        snaps, _, xd = nominal_sequence(scn, solver)
+        mpc = make_mpc(scn, _BoundsOnly(solver.bounds()))
+        seqs[name] = (mpc, snaps, xd)
+        tabs.append(mpc.ref_path.path_table())
+    J = max(t.shape[0] for t in tabs)
+    tables = np.zeros((len(tabs), J, tabs[0].shape[1]))
+    for k, t in enumerate(tabs):
+        tables[k, :t.shape[0]] = t
+        tables[k, t.shape[0]:] = t[-1]
+    out = dict(tables=tables, path_id=np.empty(count, np.int32), sector=np.empty(count, np.int32), sector_out=np.empty(count, np.int32),
+               state=np.empty((count, BoundMPC.PS_SIZE)), prev=np.empty((count, 44 * n)), x0=np.empty((count, 44 * n)),
+               p=np.empty((count, solver.np)))
+    for j in range(count):
+        i = first + j
+        name = scenario_names[i % len(scenario_names)]
+        mpc, snaps, xd = seqs[name]
+        st, sec, prev, w0, p, sec_out = builder_instance(mpc, snaps, xd, i, bound_scale)
+        out['path_id'][j], out['sector'][j], out['sector_out'][j] = names.index(name), sec, sec_out
+        out['state'][j], out['prev'][j], out['x0'][j], out['p'][j] = st, prev, w0, p
+    return out
+
+
 def _rollout(rm, w0, p, h, stages):
     """w0 with its first `stages` nodes replaced by the zero-jerk continuation of the initial
     state in p (dynamics of SURVEY App. A.4): every equality row of those nodes is zero, so

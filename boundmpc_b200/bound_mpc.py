@@ -256,6 +256,23 @@ class BoundMPC:
                    x_phi_d=x_phi_d_current, phi_max=phi_max)
         return w0, params, aux
 
+    # ------------------------------------------------------------------ inputs of the CUDA parameter builder
+    PS_SIZE = 76
+
+    def builder_state(self, q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current, bound_scale=(1.0, 1.0, 1.0, 1.0)):
+        """Per-instance state vector of `bmpc_prepare_batch` (csrc/bmpc_prepare.cuh: PS_*), the window position and
+        the previous solution: everything `prepare()` reads from this object and its arguments."""
+        st = np.zeros(self.PS_SIZE)
+        st[0:7], st[7:14], st[14:21], st[21:27], st[27:33], st[33:40] = q0, dq0, ddq0, p0, v0, jerk_current
+        st[40:44] = self.phi_current[0], self.dphi_current[0], self.ddphi_current[0], self.dddphi_current[0]
+        st[44:47], st[47:50], st[50:53] = self.pr_ref, self.iw_ref, x_phi_d
+        st[53:57] = bound_scale
+        st[57] = self.phi_max[0]
+        st[58:73] = self.weights
+        st[73] = 0.0 if self.prev_solution is None else 1.0
+        prev = np.zeros(self.N * self.nr_x) if self.prev_solution is None else np.asarray(self.prev_solution, float).ravel()
+        return st, int(self.ref_path.sector), prev
+
     # ------------------------------------------------------------------ second half of step (BoundMPC.py:454-506)
     def finish(self, sol, stats, aux, time_elapsed=0.0):
         w_curr = np.array(sol['x'], float).ravel()

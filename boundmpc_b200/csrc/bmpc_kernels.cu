@@ -11,6 +11,7 @@
 #include <new>
 #include "bmpc_host.h"
 #include "bmpc_eval.cuh"
+#include "bmpc_prepare.cuh"
 
 using namespace bmpc;
 
@@ -183,6 +184,36 @@ __global__ void __launch_bounds__(BMPC_MAX_THREADS) k_eval(const __grid_constant
              io.jac ? io.jac + b * nl * n : nullptr, io.hess ? io.hess + b * n * n : nullptr};
     eval_instance(cx, C, W, S, e);
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ parameter builder
+// k_prepare: the pre-solve half of BoundMPC.step for a batch (bmpc_prepare.cuh).  Phase 1: one thread per instance builds
+// its parameter vector (a few hundred scalar operations; rows of p are written by their owner thread).  Phase 2: the CTA
+// writes the warm starts of its instances together, consecutive threads on consecutive entries (coalesced shift copy of
+// the previous solutions).
+constexpr int PREP_THREADS = 128;
+struct PrepIO {
+  const double* tabs; int J;
+  const int32_t* path_id; int32_t* sector;
+  const double* state; const double* prev;
+  double* x0; double* p;
+};
+__global__ void __launch_bounds__(PREP_THREADS) k_prepare(const __grid_constant__ Config C, int batch, PrepIO io) {
+  __shared__ unsigned char rev[PREP_THREADS];
+  const int base = blockIdx.x * PREP_THREADS, b = base + threadIdx.x;
+  const size_t n = C.n;
+  if (b < batch) {
+    const double* st = io.state + (size_t)b * PS_SIZE;
+    io.sector[b] = prepare_params(C.L, io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW, io.J, io.sector[b], st, io.p + (size_t)b * C.np);
+    rev[threadIdx.x] = st[PS_HASPREV] != 0.0 && warm_reverse(st, io.prev + b * n);
+  }
+  __syncthreads();
+  const int cnt = batch - base < PREP_THREADS ? batch - base : PREP_THREADS;
+  for (size_t idx = threadIdx.x; idx < (size_t)cnt * n; idx += PREP_THREADS) {
+    const int i = (int)(idx / n), e = (int)(idx - (size_t)i * n), k = e / NX, a = e - NX * k;
+    const size_t bi = (size_t)(base + i);
+    io.x0[bi * n + e] = warm_start_value(C.N, io.state + bi * PS_SIZE, io.prev + bi * n, rev[i] != 0, k, a);
   }
 }
 
@@ -438,6 +469,52 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   if (kkt_err) CU(cudaMemcpyAsync(kkt_err, d + o_k, B * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(iters, d + o_it, B * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(status, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return BMPC_OK;
+}
+
+int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                       int32_t* sector, const double* state, const double* prev_x, double* x0, double* p, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_prepare_batch: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < h->C.S || !path_tables || !path_id || !sector || !state || !prev_x || !x0 || !p)
+    return fail(BMPC_E_INVALID, "bmpc_prepare_batch: invalid argument");
+  if (h->C.S > PREP_SMAX) return fail(BMPC_E_INVALID, "bmpc_prepare_batch: nr_segs above the builder's limit");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  PrepIO io{path_tables, path_rows, path_id, sector, state, prev_x, x0, p};
+  k_prepare<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                            const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x, double* x0, double* p) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_prepare_batch_host: null handle");
+  if (batch < 0 || n_paths < 1 || !path_tables || !path_id || !sector || !state || !prev_x || !x0 || !p)
+    return fail(BMPC_E_INVALID, "bmpc_prepare_batch_host: invalid argument");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, np = h->C.np, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_t = take(tb), o_id = take(B * 4), o_sec = take(B * 4), o_st = take(B * PS_SIZE * 8), o_prev = take(B * n * 8),
+               o_x0 = take(B * n * 8), o_p = take(B * np * 8);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(d + o_t, path_tables, tb, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_id, path_id, B * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_sec, sector, B * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_st, state, B * PS_SIZE * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_prev, prev_x, B * n * 8, cudaMemcpyHostToDevice, st));
+  rc = bmpc_prepare_batch(h, batch, (double*)(d + o_t), n_paths, path_rows, (int32_t*)(d + o_id), (int32_t*)(d + o_sec), (double*)(d + o_st),
+                          (double*)(d + o_prev), (double*)(d + o_x0), (double*)(d + o_p), st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(sector, d + o_sec, B * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(x0, d + o_x0, B * n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(p, d + o_p, B * np * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return BMPC_OK;
 }

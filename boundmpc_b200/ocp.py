@@ -165,6 +165,45 @@ class BatchSolver:
                                                V(kkt.data_ptr()), V(self._ws.data_ptr()), V(stream)), "bmpc_solve_batch")
         return {"x": x, "g": g, "lam_g": lg, "lam_x": lx, "f": f, "kkt": kkt, "iters": it, "status": st}
 
+    # ---- batched parameter builder (pre-solve half of BoundMPC.step)
+    PS_SIZE, PT_ROW = 76, 38
+
+    def prepare_batch(self, tables, path_id, sector, state, prev_x, out=None):
+        """tables [P, J, 38], path_id [B] int32, sector [B] int32, state [B, 76], prev_x [B, n] ->
+        dict x0 [B, n], p [B, np], sector [B] (advanced).  numpy inputs take the host-pointer entry; torch CUDA
+        tensors are processed on the current stream (sector is updated in place)."""
+        if isinstance(state, np.ndarray):
+            tables = np.ascontiguousarray(tables, np.float64)
+            state = np.ascontiguousarray(state, np.float64)
+            prev_x = np.ascontiguousarray(prev_x, np.float64)
+            pid = np.ascontiguousarray(path_id, np.int32)
+            sec = np.ascontiguousarray(sector, np.int32).copy()
+            B = state.shape[0]
+            if tables.ndim != 3 or tables.shape[2] != self.PT_ROW or state.shape != (B, self.PS_SIZE) or prev_x.shape != (B, self.n):
+                raise ValueError("prepare_batch: unexpected array shapes")
+            o = out or {}
+            x0 = o.get("x0") if "x0" in o else np.empty((B, self.n))
+            p = o.get("p") if "p" in o else np.empty((B, self.np))
+            P = _cabi.ptr
+            _cabi.check(self._lib.bmpc_prepare_batch_host(self._h, B, P(tables), tables.shape[0], tables.shape[1], P(pid), P(sec),
+                                                          P(state), P(prev_x), P(x0), P(p)), "bmpc_prepare_batch_host")
+            return {"x0": x0, "p": p, "sector": sec}
+        import torch
+        B = state.shape[0]
+        dev = state.device
+        o = out or {}
+        x0 = o["x0"] if "x0" in o else torch.empty((B, self.n), dtype=torch.float64, device=dev)
+        p = o["p"] if "p" in o else torch.empty((B, self.np), dtype=torch.float64, device=dev)
+        for t in (tables, state, prev_x, path_id, sector):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("prepare_batch: tensors must be contiguous CUDA tensors")
+        V = ctypes.c_void_p
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(self._lib.bmpc_prepare_batch(self._h, B, V(tables.data_ptr()), int(tables.shape[0]), int(tables.shape[1]),
+                                                 V(path_id.data_ptr()), V(sector.data_ptr()), V(state.data_ptr()), V(prev_x.data_ptr()),
+                                                 V(x0.data_ptr()), V(p.data_ptr()), V(stream)), "bmpc_prepare_batch")
+        return {"x0": x0, "p": p, "sector": sector}
+
     # ---- NLP function evaluation for parity tests (nlp_f / nlp_g / nlp_grad_f / nlp_jac_g / nlp_hess_l)
     def eval_batch(self, x, p, lam=None, want_jac=True, want_hess=True):
         x = np.ascontiguousarray(np.atleast_2d(x), np.float64)

@@ -142,6 +142,27 @@ class ReferencePath:
         return (self.asymm_lower, self.asymm_upper, self._window(self.bp1).T, self._window(self.bp2).T,
                 self._window(self.br1).T, self._window(self.br2).T)
 
+    # ------------------------------------------------------------------ batched parameter builder
+    PT_ROW = 38
+
+    def path_table(self):
+        """[J, 38] table of the padded path segments for the CUDA parameter builder
+        (`bmpc_prepare_batch`, csrc/bmpc_prepare.cuh: row layout PT_*).  Built once per path."""
+        J = len(self.dp)
+        T = np.zeros((J, self.PT_ROW))
+        for j in range(J):
+            T[j, 0:3] = self.p[j]
+            T[j, 3:6] = self.iw[j]
+            T[j, 6:9] = self.dp[j] / np.linalg.norm(self.dp[j])
+            T[j, 9:12] = self.dr[j]
+            T[j, 12] = self._cum[j + 1] + self.phi_bias
+            T[j, 13:15], T[j, 15:17] = self.p_lower[j], self.p_upper[j]
+            T[j, 17:19], T[j, 19:21] = self.r_lower[j], self.r_upper[j]
+            T[j, 21:24], T[j, 24:27] = self.bp1[j], self.bp2[j]
+            T[j, 27:30], T[j, 30:33] = self.br1[j], self.br2[j]
+            T[j, 33:38] = self.e_p_min[j], self.e_r_min[j], self.e_p_max[j], self.e_r_max[j], self.s[j]
+        return T
+
     def get_bound_params(self):
         return (self._window(self.e_p_min), self._window(self.e_r_min), self._window(self.e_p_max),
                 self._window(self.e_r_max), self._window(self.s))

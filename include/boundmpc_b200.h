@@ -88,6 +88,28 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
 int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g,
                           double* lam_g, double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err);
 
+/* Batched parameter builder: replaces the pre-solve half of `BoundMPC.step` (BoundMPC.py:310-443 — the window of
+ * `ReferencePath.get_parameters / get_limits / get_bound_params` (ReferencePath.py:190-238), `compute_initial_rot_errors`
+ * (utils/util_functions.py:11-31), `compute_orientation_projection_vectors` (BoundMPC.py:267-304), `compute_error_bounds`
+ * (BoundMPC.py:219-265), the warm-start shift (:316-333,373-375) and the parameter order of :416-443) for `batch`
+ * controller instances; its outputs x0, p are the inputs of bmpc_solve_batch.  DEVICE pointers, asynchronous.
+ *   path_tables [n_paths, path_rows, 38]  one row per padded path segment (layout PT_* in csrc/bmpc_prepare.cuh; built once
+ *                                         per path by boundmpc_b200.reference_path.ReferencePath.path_table())
+ *   path_id     [batch]                   path of each instance
+ *   sector      [batch]  in/out           window position (ReferencePath.sector); advanced like ReferencePath.update
+ *   state       [batch, 76]               controller state (layout PS_*: q0, dq0, ddq0, p0, v0, jerk, phi state, pr_ref,
+ *                                         iw_ref, x_phi_d, bound factors, phi_max, weights, has_prev)
+ *   prev_x      [batch, n]                previous solution (read when has_prev != 0)
+ *   x0 [batch, n], p [batch, np]          outputs
+ * The re-projection of the warm start after a path update (BoundMPC.py:335-369) is not covered. */
+int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                       const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x,
+                       double* x0, double* p, void* cuda_stream);
+/* Same with HOST pointers (copies inside, synchronises). */
+int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                            const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x,
+                            double* x0, double* p);
+
 /* Evaluation of the NLP functions for parity tests (what CasADi's nlp_f, nlp_g, nlp_grad_f,
  * nlp_jac_g, nlp_hess_l provide, casadi_ocp_formulation.py:389), HOST pointers, small batches.
  *   lam   [batch, 48 N]: per stage 36 equality multipliers then 12 interval-row multipliers

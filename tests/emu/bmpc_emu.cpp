@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../boundmpc_b200/csrc/bmpc_host.h"
 #include "../../boundmpc_b200/csrc/bmpc_eval.cuh"
+#include "../../boundmpc_b200/csrc/bmpc_prepare.cuh"
 
 using namespace bmpc;
 
@@ -61,6 +62,17 @@ int emu_solve_sliced(const bmpc_config* cfg, int batch, const double* x0, const 
   for (int b = batch - 1; b >= 0; b--)
     if (hard[b] >= 0) solve_instance(cx, C, W, *S, make_io(b), RUN_RESUME, save.data() + stride * b);
   delete S;
+  return 0;
+}
+
+// parameter builder (csrc/bmpc_prepare.cuh), serial form
+int emu_prepare(int N, int S, int batch, const double* tabs, int J, const int32_t* path_id, int32_t* sector, const double* state,
+                const double* prev, double* x0, double* p) {
+  const PLayout L = make_layout(S);
+  if (S > PREP_SMAX) return -1;
+  for (int b = 0; b < batch; b++)
+    sector[b] = prepare_instance(L, N, tabs + (size_t)path_id[b] * J * PT_ROW, J, sector[b], state + (size_t)b * PS_SIZE,
+                                 prev + (size_t)b * NX * N, x0 + (size_t)b * NX * N, p + (size_t)b * L.np);
   return 0;
 }
 

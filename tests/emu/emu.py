@@ -34,7 +34,7 @@ def make_cfg(N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
 
 def build(force=False):
     src = [os.path.join(_HERE, "bmpc_emu.cpp")] + [os.path.join(_ROOT, "boundmpc_b200", "csrc", f) for f in
-           ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h")]
+           ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h", "bmpc_prepare.cuh")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, src[0]])
     return _LIB
@@ -88,3 +88,19 @@ def evaluate(x, p, lam=None, N=10, S=4, dt=0.1, want_jac=True, want_hess=True):
     rc = lib().emu_eval(ctypes.byref(cfg), B, _p(x), _p(p), _p(lam), _p(f), _p(g), _p(d), _p(grad), _p(jac), _p(hess))
     assert rc == 0
     return dict(f=f, g=g, d=d, grad=grad, jac=jac, hess=hess)
+
+
+def prepare(tabs, path_id, sector, state, prev, N=10, S=4):
+    """Serial form of the CUDA parameter builder.  tabs [P, J, 38]; returns x0, p, new sector."""
+    tabs = np.ascontiguousarray(tabs, float)
+    state = np.ascontiguousarray(np.atleast_2d(state), float)
+    prev = np.ascontiguousarray(np.atleast_2d(prev), float)
+    B = state.shape[0]
+    pid = np.ascontiguousarray(path_id, np.int32)
+    sec = np.ascontiguousarray(sector, np.int32).copy()
+    x0, p = np.empty((B, 44 * N)), np.empty((B, 141 + 91 * S))
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().emu_prepare(N, S, B, _p(tabs), tabs.shape[1], pid.ctypes.data_as(i32p), sec.ctypes.data_as(i32p), _p(state), _p(prev),
+                           _p(x0), _p(p))
+    assert rc == 0
+    return x0, p, sec
