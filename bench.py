@@ -201,6 +201,7 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # (keeps NCCL's version banner off stdout: one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peak_dfma = solver.fp64_peak(0)
