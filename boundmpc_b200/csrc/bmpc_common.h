@@ -321,6 +321,7 @@ BMPC_DEV double dot3(const double* a, const double* b) { return a[0] * b[0] + a[
 
 // ---- block reductions: result is returned to every thread ------------------------------------
 enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+constexpr int RED_WARPS = 16;   // warps per CTA the reduction scratch is sized for (largest launch shape: 512 threads)
 
 // (one copy in the kernel image: K and the operations are run-time arguments)
 BMPC_NOINLINE void block_reduce_n(const Ctx cx, double* v, const int* op, int K) {
@@ -335,15 +336,15 @@ BMPC_NOINLINE void block_reduce_n(const Ctx cx, double* v, const int* op, int K)
       double b = __shfl_xor_sync(0xffffffffu, a, o);
       a = o_ == RED_SUM ? a + b : (o_ == RED_MAX ? fmax(a, b) : fmin(a, b));
     }
-    if (lane == 0) cx.red[k * 8 + warp] = a;
+    if (lane == 0) cx.red[k * RED_WARPS + warp] = a;
   }
   __syncthreads();
 #pragma unroll 1
   for (int k = 0; k < K; k++) {
-    double a = cx.red[k * 8];
+    double a = cx.red[k * RED_WARPS];
     const int o_ = op[k];
     for (int w = 1; w < nw; w++) {
-      double b = cx.red[k * 8 + w];
+      double b = cx.red[k * RED_WARPS + w];
       a = o_ == RED_SUM ? a + b : (o_ == RED_MAX ? fmax(a, b) : fmin(a, b));
     }
     v[k] = a;

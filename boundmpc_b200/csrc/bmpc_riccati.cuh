@@ -56,7 +56,7 @@ struct Smem {
   double tcc[NZ * 3];          // constant rows of G per column: coefficients ...
   short tcr[NZ * 3 + 4];       // ... and x-row indices (triv_col as a table)
   double alc[5], bec[5];       // d q_n / d(um, q, dq, ddq, u) and d dq_n / d(...) of the integrator (type_coef)
-  double red[8 * 8];           // block reductions (8 values x up to 8 warps)
+  double red[8 * RED_WARPS];   // block reductions (8 values x up to RED_WARPS warps)
   double filt[2 * 64];         // filter entries (theta, phi)
   int flag[4];
 #ifdef BMPC_TIMING
