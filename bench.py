@@ -294,8 +294,21 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- p50 latency of one MPC step on BASELINE configs[0]: the headless experiment1 closed loop (bound_mpc_node.py:
+    # 292-372 restated in batches.nominal_sequence), timed like the reference times its solver call (BoundMPC.py:445-455:
+    # wall clock around `self.solver(...)` + the conversion of sol['x']), one instance per call through the host entry
+    from boundmpc_b200 import batches, scenarios
+    t0 = time.perf_counter()
+    _, seq_stats, _ = batches.nominal_sequence(scenarios.experiment1(n=10), solver)
+    t_loop = (time.perf_counter() - t0) * 1e3
+    t_step = np.array([s_[1] for s_ in seq_stats]) * 1e3
+    it_step = np.array([s_[0] for s_ in seq_stats])
+    mpc_step = {"p50": float(np.percentile(t_step, 50)), "p90": float(np.percentile(t_step, 90)), "max": float(t_step.max()),
+                "steps": int(len(t_step)), "iters_mean": float(it_step.mean()), "all_converged": bool(all(s_[2] for s_ in seq_stats)),
+                "what": "experiment1 closed loop (BASELINE configs[0]), wall clock around solver(x0, p) incl. H2D/D2H, B = 1",
+                "python_pre_post_ms_per_step": float((t_loop - t_step.sum()) / len(t_step))}
+
     # ---- batched parameter builder (the pre-solve half of BoundMPC.step), rank 0
-    from boundmpc_b200 import batches
     nb = 512
     t0 = time.perf_counter()
     D = batches.make_builder_batch(solver, ("exp1", "exp2"), 0, nb, bound_scale=True)
@@ -333,6 +346,32 @@ def main():
                "parity": {"p_rel_err_vs_host_mirror": perr, "x0_bitwise_equal": x0_same, "checked": nb},
                "cpu_mirror": {"instances_per_s": nb / t_mirror, "what": "boundmpc_b200.bound_mpc.BoundMPC.prepare (numpy mirror of "
                               "BoundMPC.py:310-443) incl. controller-state restore, 1 thread"}}
+    # ---- batched post-processing (compute_return_data) and the whole batched MPC step on the device:
+    # k_prepare -> k_solve -> k_post on one stream, inputs (controller states, previous solutions) resident in HBM
+    tb["sector"].copy_(sec0)
+    so = solver.solve_batch(bo["x0"], bo["p"])
+    po = solver.post_batch(tb["tables"], tb["path_id"], tb["sector"], tb["state"], so["x"])
+    torch.cuda.synchronize()
+    p_ms, s_ms = [], []
+    for k in range(args.warmup + args.steps):
+        tb["sector"].copy_(sec0)
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        solver.prepare_batch(tb["tables"], tb["path_id"], tb["sector"], tb["state"], tb["prev"], bo)
+        solver.solve_batch(bo["x0"], bo["p"], so)
+        b.record()
+        solver.post_batch(tb["tables"], tb["path_id"], tb["sector"], tb["state"], so["x"], None, po)
+        c.record()
+        torch.cuda.synchronize()
+        if k >= args.warmup:
+            p_ms.append(b.elapsed_time(c)); s_ms.append(a.elapsed_time(c))
+    p_ms, s_ms = float(np.mean(p_ms)), float(np.mean(s_ms))
+    post_bytes = 76 * 8 + 12 + n * 8 + 10 * 42 * 8 + 76 * 8       # state, ids, w in; traj, state out
+    post = {"kernel": "k_post", "instances": per_gpu, "ms": p_ms, "instances_per_s": per_gpu / (p_ms * 1e-3),
+            "bytes_per_instance": post_bytes, "hbm": {"achieved": per_gpu * post_bytes / (p_ms * 1e-3) / 1e9, "unit": "GB/s"},
+            "mpc_step_on_device": {"ms": s_ms, "steps_per_s": per_gpu / (s_ms * 1e-3), "converged": int((so["status"] == 0).sum().item()),
+                                   "what": "k_prepare + k_solve + k_post back to back on one stream for the batch (controller states and "
+                                           "previous solutions resident in HBM); instances = 512 perturbed controller states tiled"}}
 
     sum_iters = float(cnt[1].item())
     ach = float(iters.sum()) * F_ITER[10] / (k_ms * 1e-3)          # rank 0's kernel: flop / s
@@ -344,6 +383,7 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     builder["hbm"].update(peak=hbm_peak, frac=builder["hbm"]["achieved"] / hbm_peak)
+    post["hbm"].update(peak=hbm_peak, frac=post["hbm"]["achieved"] / hbm_peak)
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_dram_bytes_per_launch")
@@ -369,6 +409,8 @@ def main():
                        "perturbation_scale_hist_rank0": {str(v): int((scale == v).sum()) for v in np.unique(scale)},
                        "input_generation_s": t_gen},
             "builder": builder,
+            "post": post,
+            "latency_mpc_step_ms": mpc_step,
             "latency_b1_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "max": float(max(lat)),
                               "what": "one instance through bmpc_solve_batch_host incl. H2D/D2H, wall clock"}}
     if world == 1 and not args.no_cpu_baseline:

@@ -12,6 +12,7 @@
 #include "bmpc_host.h"
 #include "bmpc_eval.cuh"
 #include "bmpc_prepare.cuh"
+#include "bmpc_post.cuh"
 
 using namespace bmpc;
 
@@ -216,6 +217,21 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(const __grid_constant_
     const size_t bi = (size_t)(base + i);
     io.x0[bi * n + e] = warm_start_value(C.N, io.state + bi * PS_SIZE, io.prev + bi * n, rev[i] != 0, k, a);
   }
+}
+
+// ------------------------------------------------------------------------------------------ post-processing
+// k_post: compute_return_data of BoundMPC.step for a batch (bmpc_post.cuh), one thread per instance.
+struct PostIO {
+  const double* tabs; int J;
+  const int32_t* path_id; const int32_t* sector;
+  const double* state; const double* w; const int32_t* ec;
+  double* traj; double* state_out;
+};
+__global__ void __launch_bounds__(PREP_THREADS) k_post(const __grid_constant__ Config C, int batch, PostIO io) {
+  const int b = blockIdx.x * PREP_THREADS + threadIdx.x;
+  if (b >= batch) return;
+  post_instance(C, io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW, io.sector[b], io.state + (size_t)b * PS_SIZE, io.w + (size_t)b * C.n,
+                io.ec ? io.ec[b] : 0, io.traj + (size_t)b * C.N * TR_ROW, io.state_out + (size_t)b * PS_SIZE);
 }
 
 // FP64 pipe peak probes (roofline denominator).  Each thread runs 8 independent
@@ -527,6 +543,53 @@ int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_ta
   CU(cudaMemcpyAsync(sector, d + o_sec, B * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(x0, d + o_x0, B * n * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(p, d + o_p, B * np * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return BMPC_OK;
+}
+
+int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                    const int32_t* sector, const double* state, const double* w, const int32_t* error_count, double* traj,
+                    double* state_out, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_post_batch: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !w || !traj || !state_out)
+    return fail(BMPC_E_INVALID, "bmpc_post_batch: invalid argument");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out};
+  k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                         const int32_t* sector, const double* state, const double* w, const int32_t* error_count, double* traj,
+                         double* state_out) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_post_batch_host: null handle");
+  if (batch < 0 || n_paths < 1 || !path_tables || !path_id || !sector || !state || !w || !traj || !state_out)
+    return fail(BMPC_E_INVALID, "bmpc_post_batch_host: invalid argument");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, tr = (size_t)h->C.N * TR_ROW, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_t = take(tb), o_id = take(B * 4), o_sec = take(B * 4), o_ec = take(B * 4), o_st = take(B * PS_SIZE * 8), o_w = take(B * n * 8),
+               o_tr = take(B * tr * 8), o_so = take(B * PS_SIZE * 8);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(d + o_t, path_tables, tb, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_id, path_id, B * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_sec, sector, B * 4, cudaMemcpyHostToDevice, st));
+  if (error_count) CU(cudaMemcpyAsync(d + o_ec, error_count, B * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_st, state, B * PS_SIZE * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_w, w, B * n * 8, cudaMemcpyHostToDevice, st));
+  rc = bmpc_post_batch(h, batch, (double*)(d + o_t), n_paths, path_rows, (int32_t*)(d + o_id), (int32_t*)(d + o_sec), (double*)(d + o_st),
+                       (double*)(d + o_w), error_count ? (int32_t*)(d + o_ec) : nullptr, (double*)(d + o_tr), (double*)(d + o_so), st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(traj, d + o_tr, B * tr * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(state_out, d + o_so, B * PS_SIZE * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return BMPC_OK;
 }

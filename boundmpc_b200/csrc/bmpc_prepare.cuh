@@ -35,7 +35,8 @@ enum {
   PT_RUP = 19,     // [2] r_upper_j
   PT_BP1 = 21, PT_BP2 = 24, PT_BR1 = 27, PT_BR2 = 30,   // [3] each: error bases
   PT_EB = 33,      // [5] e_p_min, e_r_min, e_p_max, e_r_max, s of segment j
-  PT_ROW = 38
+  PT_LOGR = 38,    // [3] rotation vector of the via-point rotation R_j (post-processing: rotation reference at a segment switch)
+  PT_ROW = 41
 };
 // ---- per-instance controller state (doubles)
 enum {

@@ -166,10 +166,10 @@ class BatchSolver:
         return {"x": x, "g": g, "lam_g": lg, "lam_x": lx, "f": f, "kkt": kkt, "iters": it, "status": st}
 
     # ---- batched parameter builder (pre-solve half of BoundMPC.step)
-    PS_SIZE, PT_ROW = 76, 38
+    PS_SIZE, PT_ROW = 76, 41
 
     def prepare_batch(self, tables, path_id, sector, state, prev_x, out=None):
-        """tables [P, J, 38], path_id [B] int32, sector [B] int32, state [B, 76], prev_x [B, n] ->
+        """tables [P, J, 41], path_id [B] int32, sector [B] int32, state [B, 76], prev_x [B, n] ->
         dict x0 [B, n], p [B, np], sector [B] (advanced).  numpy inputs take the host-pointer entry; torch CUDA
         tensors are processed on the current stream (sector is updated in place)."""
         if isinstance(state, np.ndarray):
@@ -203,6 +203,48 @@ class BatchSolver:
                                                  V(path_id.data_ptr()), V(sector.data_ptr()), V(state.data_ptr()), V(prev_x.data_ptr()),
                                                  V(x0.data_ptr()), V(p.data_ptr()), V(stream)), "bmpc_prepare_batch")
         return {"x0": x0, "p": p, "sector": sector}
+
+    # ---- batched post-processing (compute_return_data of BoundMPC.step)
+    TR_ROW = 42
+    TRAJ_KEYS = {"p": (0, 6), "v": (6, 12), "a": (12, 18), "q": (18, 25), "dq": (25, 32), "ddq": (32, 39), "phi": (39, 40),
+                 "dphi": (40, 41), "ddphi": (41, 42)}
+
+    def post_batch(self, tables, path_id, sector, state, w, error_count=None, out=None):
+        """tables [P, J, 41], path_id / sector [B] int32 (sector: output of prepare_batch), state [B, 76] (of this step),
+        w [B, n] (trajectory kept by the controller), error_count [B] int32 or None -> dict traj [B, N, 42] (columns
+        TRAJ_KEYS) and state [B, 76] of the next step.  numpy -> host-pointer entry, torch CUDA tensors -> current stream."""
+        if isinstance(state, np.ndarray):
+            tables = np.ascontiguousarray(tables, np.float64)
+            state = np.ascontiguousarray(state, np.float64)
+            w = np.ascontiguousarray(w, np.float64)
+            pid = np.ascontiguousarray(path_id, np.int32)
+            sec = np.ascontiguousarray(sector, np.int32)
+            ec = None if error_count is None else np.ascontiguousarray(error_count, np.int32)
+            B = state.shape[0]
+            if tables.ndim != 3 or tables.shape[2] != self.PT_ROW or state.shape != (B, self.PS_SIZE) or w.shape != (B, self.n):
+                raise ValueError("post_batch: unexpected array shapes")
+            o = out or {}
+            traj = o.get("traj") if "traj" in o else np.empty((B, self.N, self.TR_ROW))
+            so = o.get("state") if "state" in o else np.empty((B, self.PS_SIZE))
+            P = _cabi.ptr
+            _cabi.check(self._lib.bmpc_post_batch_host(self._h, B, P(tables), tables.shape[0], tables.shape[1], P(pid), P(sec), P(state),
+                                                       P(w), P(ec), P(traj), P(so)), "bmpc_post_batch_host")
+            return {"traj": traj, "state": so}
+        import torch
+        B, dev = state.shape[0], state.device
+        o = out or {}
+        traj = o["traj"] if "traj" in o else torch.empty((B, self.N, self.TR_ROW), dtype=torch.float64, device=dev)
+        so = o["state"] if "state" in o else torch.empty((B, self.PS_SIZE), dtype=torch.float64, device=dev)
+        for t in (tables, state, w, path_id, sector):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("post_batch: tensors must be contiguous CUDA tensors")
+        V = ctypes.c_void_p
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(self._lib.bmpc_post_batch(self._h, B, V(tables.data_ptr()), int(tables.shape[0]), int(tables.shape[1]),
+                                              V(path_id.data_ptr()), V(sector.data_ptr()), V(state.data_ptr()), V(w.data_ptr()),
+                                              V(error_count.data_ptr()) if error_count is not None else None, V(traj.data_ptr()),
+                                              V(so.data_ptr()), V(stream)), "bmpc_post_batch")
+        return {"traj": traj, "state": so}
 
     # ---- NLP function evaluation for parity tests (nlp_f / nlp_g / nlp_grad_f / nlp_jac_g / nlp_hess_l)
     def eval_batch(self, x, p, lam=None, want_jac=True, want_hess=True):

@@ -143,10 +143,10 @@ class ReferencePath:
                 self._window(self.br1).T, self._window(self.br2).T)
 
     # ------------------------------------------------------------------ batched parameter builder
-    PT_ROW = 38
+    PT_ROW = 41
 
     def path_table(self):
-        """[J, 38] table of the padded path segments for the CUDA parameter builder
+        """[J, 41] table of the padded path segments for the CUDA parameter builder
         (`bmpc_prepare_batch`, csrc/bmpc_prepare.cuh: row layout PT_*).  Built once per path."""
         J = len(self.dp)
         T = np.zeros((J, self.PT_ROW))
@@ -161,6 +161,7 @@ class ReferencePath:
             T[j, 21:24], T[j, 24:27] = self.bp1[j], self.bp2[j]
             T[j, 27:30], T[j, 30:33] = self.br1[j], self.br2[j]
             T[j, 33:38] = self.e_p_min[j], self.e_r_min[j], self.e_p_max[j], self.e_r_max[j], self.s[j]
+            T[j, 38:41] = log_so3(self.r[j])
         return T
 
     def get_bound_params(self):

@@ -93,7 +93,7 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
  * (utils/util_functions.py:11-31), `compute_orientation_projection_vectors` (BoundMPC.py:267-304), `compute_error_bounds`
  * (BoundMPC.py:219-265), the warm-start shift (:316-333,373-375) and the parameter order of :416-443) for `batch`
  * controller instances; its outputs x0, p are the inputs of bmpc_solve_batch.  DEVICE pointers, asynchronous.
- *   path_tables [n_paths, path_rows, 38]  one row per padded path segment (layout PT_* in csrc/bmpc_prepare.cuh; built once
+ *   path_tables [n_paths, path_rows, 41]  one row per padded path segment (layout PT_* in csrc/bmpc_prepare.cuh; built once
  *                                         per path by boundmpc_b200.reference_path.ReferencePath.path_table())
  *   path_id     [batch]                   path of each instance
  *   sector      [batch]  in/out           window position (ReferencePath.sector); advanced like ReferencePath.update
@@ -109,6 +109,26 @@ int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables,
 int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                             const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x,
                             double* x0, double* p);
+
+/* Batched post-processing: replaces `compute_return_data` of `BoundMPC.step` (BoundMPC.py:508-611,757-770, without the
+ * logging branch :614-755) for `batch` controller instances: re-integration of the joint / path-parameter trajectory from
+ * the jerks (jerk_trajectory_casadi.py:46-175), Cartesian pose / velocity / acceleration of every remaining horizon node
+ * (RobotModel.forward_kinematics, BoundMPC.py:563-579) and the controller state of the next step (path-parameter state,
+ * pr_ref, iw_ref: BoundMPC.py:593-611, utils/util_functions.py:88-99).  DEVICE pointers, asynchronous.
+ *   path_tables, path_id, state           as for bmpc_prepare_batch (state of THIS step); sector = its output
+ *   w           [batch, n]                the trajectory the controller keeps (solution x, or the previous solution
+ *                                         after a failed solve, BoundMPC.py:467-496)
+ *   error_count [batch] or NULL (= 0)     nodes of w already consumed (BoundMPC.error_count)
+ *   traj        [batch, N, 42]            per node: p(6) v(6) a(6) q(7) dq(7) ddq(7) phi dphi ddphi; rows >= N - error_count zero
+ *                                         (the jerk entries of traj_data are the columns u, u_phi of w)
+ *   state_out   [batch, 76]               state with phi .. dddphi, pr_ref, iw_ref advanced; the joint state is the caller's */
+int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                    const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
+                    const int32_t* error_count, double* traj, double* state_out, void* cuda_stream);
+/* Same with HOST pointers (copies inside, synchronises). */
+int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                         const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
+                         const int32_t* error_count, double* traj, double* state_out);
 
 /* Evaluation of the NLP functions for parity tests (what CasADi's nlp_f, nlp_g, nlp_grad_f,
  * nlp_jac_g, nlp_hess_l provide, casadi_ocp_formulation.py:389), HOST pointers, small batches.

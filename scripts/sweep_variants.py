@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 base = default_solver()
 x0, p = batches.make_batch(base, ("exp1", "exp2"), 0, B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
-for threads, ctas in [(128, 3), (160, 3), (192, 3), (256, 2)]:
+for threads, ctas in [(128, 3), (160, 3), (192, 3), (256, 2), (384, 1)]:
     os.environ["BMPC_THREADS"], os.environ["BMPC_CTAS_PER_SM"] = str(threads), str(ctas)
     try:
         s = default_solver()

@@ -9,6 +9,7 @@
 #include "../../boundmpc_b200/csrc/bmpc_host.h"
 #include "../../boundmpc_b200/csrc/bmpc_eval.cuh"
 #include "../../boundmpc_b200/csrc/bmpc_prepare.cuh"
+#include "../../boundmpc_b200/csrc/bmpc_post.cuh"
 
 using namespace bmpc;
 
@@ -73,6 +74,17 @@ int emu_prepare(int N, int S, int batch, const double* tabs, int J, const int32_
   for (int b = 0; b < batch; b++)
     sector[b] = prepare_instance(L, N, tabs + (size_t)path_id[b] * J * PT_ROW, J, sector[b], state + (size_t)b * PS_SIZE,
                                  prev + (size_t)b * NX * N, x0 + (size_t)b * NX * N, p + (size_t)b * L.np);
+  return 0;
+}
+
+// post-processing (csrc/bmpc_post.cuh), serial form
+int emu_post(const bmpc_config* cfg, int batch, const double* tabs, int J, const int32_t* path_id, const int32_t* sector, const double* state,
+             const double* w, const int32_t* ec, double* traj, double* state_out) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  for (int b = 0; b < batch; b++)
+    post_instance(C, tabs + (size_t)path_id[b] * J * PT_ROW, sector[b], state + (size_t)b * PS_SIZE, w + (size_t)b * C.n, ec[b],
+                  traj + (size_t)b * C.N * TR_ROW, state_out + (size_t)b * PS_SIZE);
   return 0;
 }
 

@@ -34,7 +34,7 @@ def make_cfg(N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
 
 def build(force=False):
     src = [os.path.join(_HERE, "bmpc_emu.cpp")] + [os.path.join(_ROOT, "boundmpc_b200", "csrc", f) for f in
-           ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h", "bmpc_prepare.cuh")]
+           ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h", "bmpc_prepare.cuh", "bmpc_post.cuh")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, src[0]])
     return _LIB
@@ -91,7 +91,7 @@ def evaluate(x, p, lam=None, N=10, S=4, dt=0.1, want_jac=True, want_hess=True):
 
 
 def prepare(tabs, path_id, sector, state, prev, N=10, S=4):
-    """Serial form of the CUDA parameter builder.  tabs [P, J, 38]; returns x0, p, new sector."""
+    """Serial form of the CUDA parameter builder.  tabs [P, J, 41]; returns x0, p, new sector."""
     tabs = np.ascontiguousarray(tabs, float)
     state = np.ascontiguousarray(np.atleast_2d(state), float)
     prev = np.ascontiguousarray(np.atleast_2d(prev), float)
@@ -104,3 +104,19 @@ def prepare(tabs, path_id, sector, state, prev, N=10, S=4):
                            _p(x0), _p(p))
     assert rc == 0
     return x0, p, sec
+
+
+def post(tabs, path_id, sector, state, w, ec, N=10, S=4, dt=0.1):
+    """Serial form of the CUDA post-processing.  Returns traj [B, N, 42] and the next-step state [B, 76]."""
+    tabs = np.ascontiguousarray(tabs, float)
+    state = np.ascontiguousarray(np.atleast_2d(state), float)
+    w = np.ascontiguousarray(np.atleast_2d(w), float)
+    B = state.shape[0]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    pid = np.ascontiguousarray(path_id, np.int32); sec = np.ascontiguousarray(sector, np.int32); e = np.ascontiguousarray(ec, np.int32)
+    traj, so = np.empty((B, N, 42)), np.empty((B, 76))
+    cfg = make_cfg(N, S, dt)
+    rc = lib().emu_post(ctypes.byref(cfg), B, _p(tabs), tabs.shape[1], pid.ctypes.data_as(i32p), sec.ctypes.data_as(i32p), _p(state), _p(w),
+                        e.ctypes.data_as(i32p), _p(traj), _p(so))
+    assert rc == 0
+    return traj, so

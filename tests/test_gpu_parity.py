@@ -104,3 +104,17 @@ def test_edge_cases(solver):
     r = solver.solve_batch(x0[None], S["p"][:1])
     assert r["status"][0] == 0
     assert rel_q_error(r["x"][0], S["x"][0]) < 1e-6
+
+
+def test_two_pass_scheduling_is_bitwise_neutral(solver, monkeypatch):
+    """Batches larger than the resident grid are solved in two passes (first slice of every instance, parked iterates
+    resumed hard-first); BMPC_SINGLE_PASS switches to the plain work queue.  Same bits either way."""
+    S1, S2 = load("seq_exp1.npz"), load("seq_exp2.npz")
+    x0 = np.tile(np.concatenate([S1["x0"], S2["x0"]]), (20, 1))      # 620 instances > 444 resident CTAs
+    p = np.tile(np.concatenate([S1["p"], S2["p"]]), (20, 1))
+    a = solver.solve_batch(x0, p)
+    monkeypatch.setenv("BMPC_SINGLE_PASS", "1")
+    b = solver.solve_batch(x0, p)
+    for k in ("x", "g", "lam_g", "lam_x", "f", "kkt", "iters", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["status"] == 0).all()
