@@ -234,6 +234,48 @@ __global__ void __launch_bounds__(PREP_THREADS) k_post(const __grid_constant__ C
                 io.ec ? io.ec[b] : 0, io.traj + (size_t)b * C.N * TR_ROW, io.state_out + (size_t)b * PS_SIZE);
 }
 
+// k_finish: second half of BoundMPC.step for a batch + closed-loop advance (bmpc_post.cuh).  Phase 1: one thread per instance
+// decides which trajectory the controller keeps, post-processes it and writes the next-step state.  Phase 2: the CTA
+// updates the previous solutions of its instances together (coalesced copy of x where the solve was accepted).
+struct FinishIO {
+  PostIO post;                 // post.w = solution x, post.ec = error count (in)
+  const double* g; const int32_t* status;
+  double* prev;                // [B, n] in/out
+  int32_t* ec_out;             // may alias post.ec
+  int advance;
+};
+__global__ void __launch_bounds__(PREP_THREADS) k_finish(const __grid_constant__ Config C, int batch, FinishIO io) {
+  __shared__ unsigned char dec[PREP_THREADS];
+  const int base = blockIdx.x * PREP_THREADS, b = base + threadIdx.x;
+  const size_t n = C.n;
+  if (b < batch) {
+    const double* st = io.post.state + (size_t)b * PS_SIZE;
+    const bool has_prev = st[PS_HASPREV] != 0.0;
+    const int d = finish_decision(C, io.status[b], io.g + (size_t)b * C.m, has_prev);
+    const int ec = d == 1 ? io.post.ec[b] + 1 : 0;
+    const double* w = d == 1 ? io.prev + b * n : io.post.w + b * n;
+    double* traj = io.post.traj + (size_t)b * C.N * TR_ROW;
+    double* so = io.post.state_out + (size_t)b * PS_SIZE;
+    if (ec < C.N) {
+      post_instance(C, io.post.tabs + (size_t)io.post.path_id[b] * io.post.J * PT_ROW, io.post.sector[b], st, w, ec, traj, so);
+      if (io.advance) advance_state(w, ec, traj, so);
+    } else {                                       // the controller gives up (BoundMPC.py:504-506): nothing to return
+      for (int i = 0; i < C.N * TR_ROW; i++) traj[i] = 0.0;
+      for (int i = 0; i < PS_SIZE; i++) so[i] = st[i];
+    }
+    if (d == 0) so[PS_HASPREV] = 1.0;
+    io.ec_out[b] = ec;
+    dec[threadIdx.x] = (unsigned char)d;
+  }
+  __syncthreads();
+  const int cnt = batch - base < PREP_THREADS ? batch - base : PREP_THREADS;
+  for (size_t idx = threadIdx.x; idx < (size_t)cnt * n; idx += PREP_THREADS) {
+    const int i = (int)(idx / n);
+    const size_t e = idx - (size_t)i * n, bi = (size_t)(base + i);
+    if (dec[i] == 0) io.prev[bi * n + e] = io.post.w[bi * n + e];
+  }
+}
+
 // FP64 pipe peak probes (roofline denominator).  Each thread runs 8 independent
 // dependency chains so the DFMA / DMMA pipe is the only limiter.
 __global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters) {
@@ -557,6 +599,22 @@ int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, in
   CU(cudaSetDevice(h->device));
   PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out};
   k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                      const int32_t* sector, const double* state, const double* x, const double* g, const int32_t* status, double* prev_x,
+                      int32_t* error_count, double* traj, double* state_out, int32_t advance, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_finish_batch: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !x || !g || !status || !prev_x ||
+      !error_count || !traj || !state_out)
+    return fail(BMPC_E_INVALID, "bmpc_finish_batch: invalid argument");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out}, g, status, prev_x, error_count, advance};
+  k_finish<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

@@ -142,4 +142,36 @@ BMPC_DEV void post_instance(const Config& C, const double* tab, int sector, cons
   st_out[PS_PHI + 3] = ujp_first;
 }
 
+// ---- second half of `BoundMPC.step` as a whole (BoundMPC.py:454-506 + compute_return_data) and the closed-loop advance of
+// bound_mpc_node.py:321-331,362.  Decision per instance:
+//   success = solver success or summed constraint violation beyond 1e-6 below 1e-4 (BoundMPC.py:461-465)
+//   success            -> keep x, it becomes the previous solution, error_count = 0
+//   failure, has prev  -> keep the previous solution, error_count + 1 (its nodes error_count.. are used)
+//   failure, no prev   -> keep x anyway, error_count = 0, no previous solution recorded
+// returns 0 / 1 / 2 for these cases.
+BMPC_DEV double constraint_violation(const Config& C, const double* g) {
+  double v = 0.0;
+  for (int i = 0; i < C.m; i++) {
+    const int r = i % NG;
+    const double gi = g[i];
+    if (gi > 1e-6) v += gi;                       // above ubg = 0
+    else if (r < NE && gi < -1e-6) v -= gi;       // below lbg = 0 (equality rows; lbg = -inf on the inequality rows)
+  }
+  return v;
+}
+BMPC_DEV int finish_decision(const Config& C, int status, const double* g, bool has_prev) {
+  const bool success = status == ST_SUCCESS || constraint_violation(C, g) < 1e-4;
+  return success ? 0 : (has_prev ? 1 : 2);
+}
+// The controller state after the robot has moved by one sample under the first jerk of the kept trajectory
+// (integrate_joint, utils/util_functions.py:152-161, = node 0 of the post-processed trajectory): joint state, pose,
+// Cartesian velocity and applied jerk replace the measured ones in the next-step state of post_instance.
+BMPC_DEV void advance_state(const double* w, int ec, const double* traj, double* st_out) {
+  for (int j = 0; j < 7; j++) {
+    st_out[PS_Q + j] = traj[TR_Q + j]; st_out[PS_DQ + j] = traj[TR_DQ + j]; st_out[PS_DDQ + j] = traj[TR_DDQ + j];
+    st_out[PS_JERK + j] = w[NX * ec + oU + j];
+  }
+  for (int a = 0; a < 6; a++) { st_out[PS_P0 + a] = traj[TR_P + a]; st_out[PS_V0 + a] = traj[TR_V + a]; }
+}
+
 }  // namespace bmpc

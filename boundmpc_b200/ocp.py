@@ -246,6 +246,24 @@ class BatchSolver:
                                               V(so.data_ptr()), V(stream)), "bmpc_post_batch")
         return {"traj": traj, "state": so}
 
+    def finish_batch(self, tables, path_id, sector, state, sol, prev_x, error_count, advance=True, out=None):
+        """Second half of BoundMPC.step for a batch on the device (torch CUDA tensors): accept / reject every solve of
+        `sol` (dict of solve_batch), keep the previous solution where rejected, post-process and (advance=True) move the
+        robot by one sample.  prev_x [B, n] and error_count [B] int32 are updated in place.  -> dict traj, state."""
+        import torch
+        B, dev = state.shape[0], state.device
+        o = out or {}
+        traj = o["traj"] if "traj" in o else torch.empty((B, self.N, self.TR_ROW), dtype=torch.float64, device=dev)
+        so = o["state"] if "state" in o else torch.empty((B, self.PS_SIZE), dtype=torch.float64, device=dev)
+        V = ctypes.c_void_p
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(self._lib.bmpc_finish_batch(self._h, B, V(tables.data_ptr()), int(tables.shape[0]), int(tables.shape[1]),
+                                                V(path_id.data_ptr()), V(sector.data_ptr()), V(state.data_ptr()), V(sol["x"].data_ptr()),
+                                                V(sol["g"].data_ptr()), V(sol["status"].data_ptr()), V(prev_x.data_ptr()),
+                                                V(error_count.data_ptr()), V(traj.data_ptr()), V(so.data_ptr()), int(bool(advance)),
+                                                V(stream)), "bmpc_finish_batch")
+        return {"traj": traj, "state": so}
+
     # ---- NLP function evaluation for parity tests (nlp_f / nlp_g / nlp_grad_f / nlp_jac_g / nlp_hess_l)
     def eval_batch(self, x, p, lam=None, want_jac=True, want_hess=True):
         x = np.ascontiguousarray(np.atleast_2d(x), np.float64)

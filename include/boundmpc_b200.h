@@ -125,7 +125,19 @@ int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_ta
 int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                     const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
                     const int32_t* error_count, double* traj, double* state_out, void* cuda_stream);
-/* Same with HOST pointers (copies inside, synchronises). */
+/* Second half of `BoundMPC.step` as a whole (BoundMPC.py:454-506) for a batch, optionally with the closed-loop advance of
+ * bound_mpc_node.py:321-331,362 — the step of an on-device roll-out (with bmpc_prepare_batch and bmpc_solve_batch, no host
+ * round trip).  Per instance: the solve is accepted if status == 0 or the summed constraint violation beyond 1e-6 is below
+ * 1e-4 (BoundMPC.py:461-465); an accepted x becomes the previous solution (prev_x, error_count = 0); after a rejected solve
+ * the previous solution is kept and error_count incremented (its nodes error_count.. are post-processed); traj / state_out as
+ * for bmpc_post_batch.  advance != 0: state_out also carries the joint state, pose, Cartesian velocity and applied jerk after
+ * one sample under the first kept jerk (integrate_joint, utils/util_functions.py:152-161), i.e. it is the input state of the
+ * next bmpc_prepare_batch.  DEVICE pointers, asynchronous.  prev_x [batch, n] and error_count [batch] are updated in place. */
+int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                      const int32_t* path_id, const int32_t* sector, const double* state, const double* x, const double* g,
+                      const int32_t* status, double* prev_x, int32_t* error_count, double* traj, double* state_out,
+                      int32_t advance, void* cuda_stream);
+/* bmpc_post_batch with HOST pointers (copies inside, synchronises). */
 int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                          const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
                          const int32_t* error_count, double* traj, double* state_out);

@@ -88,6 +88,31 @@ int emu_post(const bmpc_config* cfg, int batch, const double* tabs, int J, const
   return 0;
 }
 
+// second half of BoundMPC.step + closed-loop advance (k_finish of bmpc_kernels.cu, serial form)
+int emu_finish(const bmpc_config* cfg, int batch, const double* tabs, int J, const int32_t* path_id, const int32_t* sector, const double* state,
+               const double* x, const double* g, const int32_t* status, double* prev, int32_t* ec, double* traj, double* state_out, int advance) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  for (int b = 0; b < batch; b++) {
+    const double* st = state + (size_t)b * PS_SIZE;
+    const int d = finish_decision(C, status[b], g + (size_t)b * C.m, st[PS_HASPREV] != 0.0);
+    const int e = d == 1 ? ec[b] + 1 : 0;
+    const double* w = d == 1 ? prev + (size_t)b * C.n : x + (size_t)b * C.n;
+    double* T = traj + (size_t)b * C.N * TR_ROW;
+    double* so = state_out + (size_t)b * PS_SIZE;
+    if (e < C.N) {
+      post_instance(C, tabs + (size_t)path_id[b] * J * PT_ROW, sector[b], st, w, e, T, so);
+      if (advance) advance_state(w, e, T, so);
+    } else {
+      for (int i = 0; i < C.N * TR_ROW; i++) T[i] = 0.0;
+      for (int i = 0; i < PS_SIZE; i++) so[i] = st[i];
+    }
+    if (d == 0) { so[PS_HASPREV] = 1.0; memcpy(prev + (size_t)b * C.n, x + (size_t)b * C.n, sizeof(double) * C.n); }
+    ec[b] = e;
+  }
+  return 0;
+}
+
 int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p, const double* lam, double* f, double* g,
              double* d, double* grad, double* jac, double* hess) {
   Config C;

@@ -120,3 +120,21 @@ def post(tabs, path_id, sector, state, w, ec, N=10, S=4, dt=0.1):
                         e.ctypes.data_as(i32p), _p(traj), _p(so))
     assert rc == 0
     return traj, so
+
+
+def finish(tabs, path_id, sector, state, x, g, status, prev, ec, advance=True, N=10, S=4, dt=0.1):
+    """Serial form of k_finish.  Returns traj, next state, updated prev and error counts."""
+    tabs = np.ascontiguousarray(tabs, float)
+    state = np.ascontiguousarray(np.atleast_2d(state), float)
+    x = np.ascontiguousarray(np.atleast_2d(x), float); g = np.ascontiguousarray(np.atleast_2d(g), float)
+    prev = np.ascontiguousarray(np.atleast_2d(prev), float).copy()
+    B = state.shape[0]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    pid = np.ascontiguousarray(path_id, np.int32); sec = np.ascontiguousarray(sector, np.int32)
+    st = np.ascontiguousarray(status, np.int32); e = np.ascontiguousarray(ec, np.int32).copy()
+    traj, so = np.empty((B, N, 42)), np.empty((B, 76))
+    cfg = make_cfg(N, S, dt)
+    rc = lib().emu_finish(ctypes.byref(cfg), B, _p(tabs), tabs.shape[1], pid.ctypes.data_as(i32p), sec.ctypes.data_as(i32p), _p(state), _p(x),
+                          _p(g), st.ctypes.data_as(i32p), _p(prev), e.ctypes.data_as(i32p), _p(traj), _p(so), int(advance))
+    assert rc == 0
+    return traj, so, prev, e

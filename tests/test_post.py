@@ -59,6 +59,56 @@ def test_post_matches_host_mirror_along_the_closed_loop(name, steps):
     assert len(sectors) >= 2          # the rotation reference went through at least one segment switch
 
 
+def test_closed_loop_on_builder_solver_finish_matches_host_mirror():
+    """The three device stages of a roll-out step (host builds: emu.prepare -> solver -> emu.finish with advance) against
+    the mirror's `BoundMPC.step` + `integrate_joint` loop, including a rejected solve (fallback on the previous solution,
+    BoundMPC.py:467-496) and the steps after it."""
+    s = EmuSolver()
+    scn = scenarios.experiment2(n=10)
+    mpc = batches.make_mpc(scn, s)
+    tab = mpc.ref_path.path_table()[None]
+    rm = RobotModel()
+    q, dq, ddq, jerk, v = scn['q0'].copy(), np.zeros(7), np.zeros(7), np.zeros(7), np.zeros(6)
+    x_phi_d = np.array([mpc.phi_max[0], 0.0, 0.0])
+    from boundmpc_b200.rollout import initial_state
+    st, sector, prev = initial_state(mpc, scn['q0'])
+    st, prev, sec, ec = st[None].copy(), prev[None].copy(), np.array([sector], np.int32), np.array([0], np.int32)
+    for step in range(30):
+        # device-form step
+        x0, p, sec = emu.prepare(tab, [0], sec, st, prev)
+        r = s.solve_batch(x0, p)
+        status, g = r["status"].copy(), r["g"].copy()
+        fail = step in (7, 8)
+        if fail:                                 # pretend the solver failed and left a violated point
+            status[:] = 1
+            g[0, 3] = 0.5
+        traj_d, st_next, prev, ec = emu.finish(tab, [0], sec, st, r["x"], g, status, prev, ec)
+        # mirror step from the same measured state
+        p_lie = rm.fk(q)
+        w0, params, aux = mpc.prepare(q, dq, ddq, p_lie, v, x_phi_d, jerk)
+        assert np.abs(w0 - x0[0]).max() < 1e-5          # warm starts: shifted previous solutions of the two loops
+        sol = mpc.solver(x0=w0, lbx=mpc.lbu, ubx=mpc.ubu, lbg=mpc.lbg, ubg=mpc.ubg, p=params)
+        stats = mpc.solver.stats()
+        if fail:
+            stats = dict(stats, success=False)
+            sol = dict(sol, g=g[0])
+        traj, _, _, _, _ = mpc.finish(sol, stats, aux)
+        M = 10 - mpc.error_count
+        assert ec[0] == mpc.error_count
+        assert _compare(traj_d[0], traj, M) < 1e-6
+        jm = np.concatenate((jerk[:, None], traj['dddq'][:, :2]), axis=1)
+        q, dq, ddq, p_lie, v, _, _ = integrate_joint(rm, jm, q, dq, ddq, mpc.dt)
+        jerk = traj['dddq'][:, 0].copy()
+        # the advanced device state is the mirror's next measured state and controller state
+        # (the two loops solve separately from inputs that differ in the last bits; the jerk is the soft direction)
+        assert np.abs(st_next[0, 0:7] - q).max() < 1e-8 and np.abs(st_next[0, 7:14] - dq).max() < 1e-7
+        assert np.abs(st_next[0, 21:27] - p_lie).max() < 1e-8 and np.abs(st_next[0, 27:33] - v).max() < 1e-7
+        assert np.abs(st_next[0, 33:40] - jerk).max() < 1e-5
+        assert abs(st_next[0, 40] - mpc.phi_current[0]) < 1e-8 and np.abs(st_next[0, 44:47] - mpc.pr_ref).max() < 1e-8
+        st = st_next
+    assert mpc.error_count == 0 and step == 29
+
+
 @pytest.mark.gpu
 def test_gpu_post_matches_host_build():
     import torch
@@ -77,3 +127,36 @@ def test_gpu_post_matches_host_build():
          dict(tables=D["tables"], path_id=D["path_id"], sector=D["sector_out"], state=D["state"], w=w, ec=ec).items()}
     rd = s.post_batch(t["tables"], t["path_id"], t["sector"], t["state"], t["w"], t["ec"])
     assert np.array_equal(rd["traj"].cpu().numpy(), r["traj"]) and np.array_equal(rd["state"].cpu().numpy(), r["state"])
+
+
+@pytest.mark.gpu
+def test_gpu_rollout_follows_the_host_mirror_closed_loop():
+    """On-device roll-out (prepare -> solve -> finish on one stream) of both experiments against the
+    nominal closed loop of the host mirror driven by the same CUDA solver."""
+    import torch
+    from boundmpc_b200.ocp import default_solver
+    from boundmpc_b200.rollout import initial_state, rollout
+    s = default_solver()
+    steps, dev = 40, torch.device("cuda")
+    tabs, states, sectors, refs = [], [], [], []
+    for name in ("exp1", "exp2"):
+        scn = scenarios.experiment1(n=10) if name == "exp1" else scenarios.experiment2(n=10)
+        mpc = batches.make_mpc(scn, s)
+        tabs.append(mpc.ref_path.path_table())
+        st, sector, _ = initial_state(mpc, scn['q0'])
+        states.append(st); sectors.append(sector)
+        snaps, stats, _ = batches.nominal_sequence(scn, s, max_steps=steps + 1)
+        refs.append((np.stack([sn[1]['q'] for sn in snaps[1:steps + 1]]), [st_[0] for st_ in stats[:steps]]))
+    J = max(t.shape[0] for t in tabs)
+    T = np.zeros((2, J, 41))
+    for k, t in enumerate(tabs):
+        T[k, :t.shape[0]] = t
+        T[k, t.shape[0]:] = t[-1]
+    out = rollout(s, torch.from_numpy(T).to(dev), torch.tensor([0, 1], dtype=torch.int32, device=dev),
+                  torch.from_numpy(np.stack(states)).to(dev), torch.tensor(sectors, dtype=torch.int32, device=dev), steps)
+    assert int(out["status"].abs().sum()) == 0 and int(out["error_count"].sum()) == 0
+    q = out["q"].cpu().numpy()                    # [steps, 2, 7]: joint position after each step
+    for k in range(2):
+        assert np.abs(q[:, k] - refs[k][0]).max() < 1e-6
+        it = np.array(out["iters"][:, k].cpu().tolist()) - np.array(refs[k][1])      # (inputs differ in the last bits)
+        assert (it == 0).mean() >= 0.9 and np.abs(it).max() <= 2
