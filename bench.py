@@ -366,6 +366,32 @@ def main():
         if k >= args.warmup:
             p_ms.append(b.elapsed_time(c)); s_ms.append(a.elapsed_time(c))
     p_ms, s_ms = float(np.mean(p_ms)), float(np.mean(s_ms))
+    # ---- on-device closed loop: per_gpu robots from the start of both experiments, per-robot bound widths
+    from boundmpc_b200.rollout import initial_state, rollout
+    r_st, r_sec = [], []
+    for nm in ("exp1", "exp2"):
+        scn_ = scenarios.experiment1(n=10) if nm == "exp1" else scenarios.experiment2(n=10)
+        m_ = batches.make_mpc(scn_, batches._BoundsOnly(solver.bounds()))
+        st_, sec_, _ = initial_state(m_, scn_['q0'])
+        r_st.append(st_); r_sec.append(sec_)
+    r_pid = (np.arange(per_gpu) % 2).astype(np.int32)
+    r_state = np.stack([r_st[k] for k in r_pid])
+    r_state[:, 53:57] = np.random.default_rng(20261017).uniform(1.0, 1.25, (per_gpu, 4))
+    r_args = (solver, tb["tables"], torch.from_numpy(r_pid).to(dev), torch.from_numpy(r_state).to(dev),
+              torch.from_numpy(np.array([r_sec[k] for k in r_pid], np.int32)).to(dev))
+    r_steps = 16
+    rollout(*r_args, 2, record=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ro = rollout(*r_args, r_steps, record=True)
+    torch.cuda.synchronize()
+    r_el = time.perf_counter() - t0
+    roll = {"robots": per_gpu, "steps": r_steps, "wall_ms": r_el * 1e3, "mpc_steps_per_s": per_gpu * r_steps / r_el,
+            "converged_frac": float((ro["status"] == 0).float().mean().item()), "iters_mean": float(ro["iters"].float().mean().item()),
+            "kernel_launches_per_step": 3,
+            "what": "closed loop of bound_mpc_node.py:292-372 for a batch on the device: k_prepare -> k_solve -> k_finish per step, "
+                    "state resident in HBM, host only enqueues; robots start at the initial state of experiment1 / experiment2 with "
+                    "bound widths x U(1, 1.25)"}
     post_bytes = 76 * 8 + 12 + n * 8 + 10 * 42 * 8 + 76 * 8       # state, ids, w in; traj, state out
     post = {"kernel": "k_post", "instances": per_gpu, "ms": p_ms, "instances_per_s": per_gpu / (p_ms * 1e-3),
             "bytes_per_instance": post_bytes, "hbm": {"achieved": per_gpu * post_bytes / (p_ms * 1e-3) / 1e9, "unit": "GB/s"},
@@ -410,6 +436,7 @@ def main():
                        "input_generation_s": t_gen},
             "builder": builder,
             "post": post,
+            "rollout": roll,
             "latency_mpc_step_ms": mpc_step,
             "latency_b1_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "max": float(max(lat)),
                               "what": "one instance through bmpc_solve_batch_host incl. H2D/D2H, wall clock"}}
