@@ -226,12 +226,20 @@ struct PostIO {
   const int32_t* path_id; const int32_t* sector;
   const double* state; const double* w; const int32_t* ec;
   double* traj; double* state_out;
+  const double* p; double* ref; double* err;      // logging branch (reference data, error terms): all three or none
 };
 __global__ void __launch_bounds__(PREP_THREADS) k_post(const __grid_constant__ Config C, int batch, PostIO io) {
   const int b = blockIdx.x * PREP_THREADS + threadIdx.x;
   if (b >= batch) return;
-  post_instance(C, io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW, io.sector[b], io.state + (size_t)b * PS_SIZE, io.w + (size_t)b * C.n,
-                io.ec ? io.ec[b] : 0, io.traj + (size_t)b * C.N * TR_ROW, io.state_out + (size_t)b * PS_SIZE);
+  const double* tab = io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW;
+  const double* st = io.state + (size_t)b * PS_SIZE;
+  const int ec = io.ec ? io.ec[b] : 0;
+  double* traj = io.traj + (size_t)b * C.N * TR_ROW;
+  double* so = io.state_out + (size_t)b * PS_SIZE;
+  post_instance(C, tab, io.sector[b], st, io.w + (size_t)b * C.n, ec, traj, so);
+  if (io.ref)
+    log_instance(C, tab, io.sector[b], st, io.p + (size_t)b * C.np, traj, ec, so + PS_PRREF, io.ref + (size_t)b * C.N * RF_ROW,
+                 io.err + (size_t)b * C.N * ER_ROW);
 }
 
 // k_finish: second half of BoundMPC.step for a batch + closed-loop advance (bmpc_post.cuh).  Phase 1: one thread per instance
@@ -597,7 +605,23 @@ int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, in
     return fail(BMPC_E_INVALID, "bmpc_post_batch: invalid argument");
   if (batch == 0) return BMPC_OK;
   CU(cudaSetDevice(h->device));
-  PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out};
+  PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out, nullptr, nullptr, nullptr};
+  k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_post_log_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                        const int32_t* sector, const double* state, const double* p, const double* w, const int32_t* error_count, double* traj,
+                        double* state_out, double* ref, double* err, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_post_log_batch: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < 3 || !path_tables || !path_id || !sector || !state || !p || !w || !traj || !state_out || !ref || !err)
+    return fail(BMPC_E_INVALID, "bmpc_post_log_batch: invalid argument");
+  if (h->C.S < 3) return fail(BMPC_E_INVALID, "bmpc_post_log_batch: the rotation reference of the logging branch needs nr_segs >= 3");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out, p, ref, err};
   k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
   h->launches += 1;
@@ -613,7 +637,8 @@ int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, 
     return fail(BMPC_E_INVALID, "bmpc_finish_batch: invalid argument");
   if (batch == 0) return BMPC_OK;
   CU(cudaSetDevice(h->device));
-  FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out}, g, status, prev_x, error_count, advance};
+  FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out, nullptr, nullptr, nullptr}, g, status, prev_x,
+              error_count, advance};
   k_finish<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
   h->launches += 1;

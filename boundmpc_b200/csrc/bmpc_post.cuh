@@ -142,6 +142,122 @@ BMPC_DEV void post_instance(const Config& C, const double* tab, int sector, cons
   st_out[PS_PHI + 3] = ujp_first;
 }
 
+// ---- logging branch of compute_return_data (BoundMPC.py:614-755): reference data and error terms per node.
+// Everything it needs beyond the trajectory is in the parameter vector p the builder produced (reference window, bound
+// coefficients, projection vectors, SO(3) Jacobians, initial rotation errors).
+enum { RF_P = 0, RF_DP = 6, RF_DDP = 12, RF_DPN = 18, RF_RPAR = 21, RF_LO = 22, RF_UP = 26, RF_EPOFF = 30, RF_EROFF = 32,
+       RF_BP1 = 34, RF_BP2 = 37, RF_BR1 = 40, RF_BR2 = 43, RF_V1 = 46, RF_V2 = 49, RF_V3 = 52, RF_ROW = 55 };
+enum { ER_EP = 0, ER_DEP = 3, ER_EPPAR = 6, ER_EPORTH = 9, ER_DEPPAR = 12, ER_DEPORTH = 15, ER_ER = 18, ER_DER = 21, ER_ERPAR = 24,
+       ER_ERO1 = 27, ER_ERO2 = 30, ER_ROW = 33 };
+
+// `prn` = rotation reference after this step's update (state_out[PS_PRREF]); traj = output of post_instance
+BMPC_DEV void log_instance(const Config& C, const double* tab, int sector, const double* st, const double* p, const double* traj, int ec,
+                           const double* prn, double* ref, double* err) {
+  const PLayout& L = C.L;
+  const int N = C.N, M = N - ec, S = L.S;
+  const double h = C.dt;
+  const double* ps = p + L.phisw;
+  double jl[9], jr[9], d0[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) { jl[3 * r + c] = p[L.jacl + 3 * c + r]; jr[3 * r + c] = p[L.jacr + 3 * c + r]; }
+  for (int a = 0; a < 3; a++) d0[a] = p[L.dtau + a];
+  const double* p0 = st + PS_P0;
+  // integrated angular velocity along the horizon (BoundMPC.py:573-585); omega before the first node = J(q0) dq0
+  double om_prev[3], iw[3];
+  {
+    double pose[6], v0[6], a0[6];
+    rm_node(st + PS_Q, st + PS_DQ, st + PS_DDQ, pose, v0, a0);
+    for (int a = 0; a < 3; a++) { om_prev[a] = v0[3 + a]; iw[a] = p0[3 + a]; }
+  }
+  double sign = 1.0;
+  for (int i = 0; i < N; i++) {
+    double* R = ref + (size_t)i * RF_ROW;
+    double* E = err + (size_t)i * ER_ROW;
+    if (i >= M) { for (int a = 0; a < RF_ROW; a++) R[a] = 0.0; for (int a = 0; a < ER_ROW; a++) E[a] = 0.0; continue; }
+    const double* T = traj + (size_t)i * TR_ROW;
+    for (int a = 0; a < 3; a++) { iw[a] += 0.5 * h * (om_prev[a] + T[TR_V + 3 + a]); om_prev[a] = T[TR_V + 3 + a]; }
+    if (i == 0 && ec > 0) {                                    // BoundMPC.py:586-588 (the flip acts on the whole horizon)
+      double dd = 0.0;
+      for (int a = 0; a < 3; a++) dd += (p0[3 + a] - iw[a]) * (p0[3 + a] - iw[a]);
+      if (sqrt(dd) > 3.1) sign = -1.0;
+    }
+    const double oiw[3] = {sign * iw[0], sign * iw[1], sign * iw[2]};
+    const double phi = T[TR_PHI], dphi = T[TR_PHI + 1];
+    // reference_function on numbers (bound_mpc_functions.py:43-149; index rules SURVEY App. B.1-B.3)
+    int si = S - 1;
+    for (int q = S - 2; q >= 0; q--) if (phi < ps[q + 1]) si = q;
+    const int jb = si < S - 2 ? si : S - 2, rr = phi < ps[S] ? si : S;
+    const double tau = phi - ps[si];
+    double b[9];
+    for (int j = 0; j < 9; j++) {
+      const int o = j * (S + 1) + rr;
+      b[j] = (((p[L.a4 + o] * tau + p[L.a3 + o]) * tau + p[L.a2 + o]) * tau + p[L.a1 + o]) * tau + p[L.a0 + o];
+    }
+    double pd[6], dpd[6];
+    for (int k = 0; k < 6; k++) { dpd[k] = p[L.dpref + k * S + si]; pd[k] = p[L.pref + k * S + si] + dpd[k] * tau; }
+    for (int k = 0; k < 6; k++) { R[RF_P + k] = pd[k]; R[RF_DP + k] = dpd[k]; R[RF_DDP + k] = 0.0; }
+    double dpn[3], v1[3], v2[3], v3[3], br1[3], br2[3];
+    for (int k = 0; k < 3; k++) {
+      dpn[k] = p[L.dpn + k * S + si]; v1[k] = p[L.v1 + k * S + si]; v2[k] = p[L.v2 + k * S + si]; v3[k] = p[L.v3 + k * S + si];
+      br1[k] = p[L.br1 + k * S + si]; br2[k] = p[L.br2 + k * S + si];
+      R[RF_DPN + k] = dpn[k]; R[RF_BP1 + k] = p[L.bp1 + k * S + jb]; R[RF_BP2 + k] = p[L.bp2 + k * S + jb];
+      R[RF_BR1 + k] = br1[k]; R[RF_BR2 + k] = br2[k]; R[RF_V1 + k] = v1[k]; R[RF_V2 + k] = v2[k]; R[RF_V3 + k] = v3[k];
+    }
+    R[RF_RPAR] = b[8];
+    R[RF_LO] = b[2]; R[RF_LO + 1] = b[3]; R[RF_LO + 2] = b[6]; R[RF_LO + 3] = b[7];
+    R[RF_UP] = b[0]; R[RF_UP + 1] = b[1]; R[RF_UP + 2] = b[4]; R[RF_UP + 3] = b[5];
+    R[RF_EPOFF] = 0.5 * (b[0] + b[2]); R[RF_EPOFF + 1] = 0.5 * (b[1] + b[3]);
+    R[RF_EROFF] = 0.5 * (b[4] + b[6]); R[RF_EROFF + 1] = 0.5 * (b[5] + b[7]);
+    // error_function (bound_mpc_functions.py:152-202)
+    const double* t = dpd;
+    const double* wr = dpd + 3;
+    double ep[3], dep[3], x1[3], x2[3], er[3], der[3];
+    for (int k = 0; k < 3; k++) { ep[k] = T[TR_P + k] - pd[k]; dep[k] = T[TR_V + k] - t[k] * dphi; }
+    const double te = dot3(t, ep), tde = dot3(t, dep);
+    for (int k = 0; k < 3; k++) { x1[k] = oiw[k] - p0[3 + k]; x2[k] = pd[3 + k] - st[PS_IWREF + k]; }
+    double y1[3], y2[3], y3[3], y4[3], wd[3];
+    m3_vec(jl, x1, y1); m3_vec(jr, x2, y2);
+    for (int k = 0; k < 3; k++) wd[k] = wr[k] * dphi;
+    m3_vec(jl, T + TR_V + 3, y3); m3_vec(jr, wd, y4);
+    double dd[3];
+    for (int k = 0; k < 3; k++) { er[k] = d0[k] + y1[k] - y2[k]; der[k] = y3[k] - y4[k]; dd[k] = er[k] - d0[k]; }
+    const double s1 = dot3(dd, v1), s2 = dot3(dd, v2), s3 = dot3(dd, v3);
+    for (int k = 0; k < 3; k++) {
+      E[ER_EP + k] = ep[k]; E[ER_DEP + k] = dep[k];
+      E[ER_EPPAR + k] = te * t[k]; E[ER_EPORTH + k] = ep[k] - te * t[k];
+      E[ER_DEPPAR + k] = tde * t[k]; E[ER_DEPORTH + k] = dep[k] - tde * t[k];
+      E[ER_ER + k] = er[k]; E[ER_DER + k] = der[k];
+      E[ER_ERPAR + k] = p[L.par + 3 * si + k] + s2 * dpn[k];
+      E[ER_ERO1 + k] = p[L.orth1 + 3 * si + k] + s1 * br1[k];
+      E[ER_ERO2 + k] = p[L.orth2 + 3 * si + k] + s3 * br2[k];
+    }
+  }
+  // exact rotation reference / error along the horizon (BoundMPC.py:716-752)
+  const double* row0 = tab + (size_t)sector * PT_ROW;
+  double pr[3] = {prn[0], prn[1], prn[2]};
+  for (int i = 0; i < M; i++) {
+    double* R = ref + (size_t)i * RF_ROW;
+    double* E = err + (size_t)i * ER_ROW;
+    const double* T = traj + (size_t)i * TR_ROW;
+    double Ra[9], Rb[9], Rc[9];
+    for (int a = 0; a < 3; a++) R[RF_P + 3 + a] = pr[a];
+    so3_exp(T + TR_P + 3, Ra);
+    so3_exp(pr, Rb);
+    m3_mul_bt(Ra, Rb, Rc);
+    so3_log(Rc, E + ER_ER);
+    if (i + 1 < M) {
+      const double phi = T[TR_PHI], nxt = T[TR_ROW + TR_PHI];
+      double out[3];
+      if (nxt > ps[1] && phi < ps[1]) integrate_rot_ref(row0 + PT_ROW + PT_LOGR, row0 + PT_ROW + PT_DR, ps[1], nxt, out);
+      else if (nxt > ps[2] && phi < ps[2]) integrate_rot_ref(row0 + 2 * PT_ROW + PT_LOGR, row0 + 2 * PT_ROW + PT_DR, ps[2], nxt, out);
+      else if (nxt > ps[2]) integrate_rot_ref(pr, row0 + 2 * PT_ROW + PT_DR, phi, nxt, out);
+      else if (nxt > ps[1]) integrate_rot_ref(pr, row0 + PT_ROW + PT_DR, phi, nxt, out);
+      else integrate_rot_ref(pr, row0 + PT_DR, phi, nxt, out);
+      for (int a = 0; a < 3; a++) pr[a] = out[a];
+    }
+  }
+}
+
 // ---- second half of `BoundMPC.step` as a whole (BoundMPC.py:454-506 + compute_return_data) and the closed-loop advance of
 // bound_mpc_node.py:321-331,362.  Decision per instance:
 //   success = solver success or summed constraint violation beyond 1e-6 below 1e-4 (BoundMPC.py:461-465)

@@ -47,6 +47,7 @@ class BatchSolver:
         cfg.mu_init = float(opts.get("mu_init", 0.0))
         cfg.bound_push = float(opts.get("warm_start_bound_push", 0.0))
         cfg.device = int(device)
+        self._device = int(device)
         cfg.threads = int((solver_opts or {}).get("b200", {}).get("threads", 0))
         self._lib = _cabi.lib()
         h = ctypes.c_void_p()
@@ -245,6 +246,31 @@ class BatchSolver:
                                               V(error_count.data_ptr()) if error_count is not None else None, V(traj.data_ptr()),
                                               V(so.data_ptr()), V(stream)), "bmpc_post_batch")
         return {"traj": traj, "state": so}
+
+    RF_ROW, ER_ROW = 55, 33
+    ERR_KEYS = ("e_p", "de_p", "e_p_par", "e_p_orth", "de_p_par", "de_p_orth", "e_r", "de_r", "e_r_par", "e_r_orth1", "e_r_orth2")
+
+    def post_log_batch(self, tables, path_id, sector, state, p, w, error_count=None):
+        """post_batch plus the logging branch (ref_data / err_data of BoundMPC.step).  numpy or torch CUDA inputs; returns
+        dict traj [B, N, 42], state [B, 76], ref [B, N, 55], err [B, N, 33] (err columns: ERR_KEYS, 3 each) of the same kind."""
+        import torch
+        host = isinstance(state, np.ndarray)
+        dev = (torch.device("cuda", self._device) if self._device >= 0 else torch.device("cuda")) if host else state.device
+        T = (lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)) if host else (lambda a, dt=None: a)
+        tables, state, p, w = T(tables, np.float64), T(state, np.float64), T(p, np.float64), T(w, np.float64)
+        path_id, sector = T(path_id, np.int32), T(sector, np.int32)
+        ec = None if error_count is None else T(error_count, np.int32)
+        B = state.shape[0]
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+        traj, so, ref, err = mk(B, self.N, self.TR_ROW), mk(B, self.PS_SIZE), mk(B, self.N, self.RF_ROW), mk(B, self.N, self.ER_ROW)
+        V = ctypes.c_void_p
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(self._lib.bmpc_post_log_batch(self._h, B, V(tables.data_ptr()), int(tables.shape[0]), int(tables.shape[1]),
+                                                  V(path_id.data_ptr()), V(sector.data_ptr()), V(state.data_ptr()), V(p.data_ptr()),
+                                                  V(w.data_ptr()), V(ec.data_ptr()) if ec is not None else None, V(traj.data_ptr()),
+                                                  V(so.data_ptr()), V(ref.data_ptr()), V(err.data_ptr()), V(stream)), "bmpc_post_log_batch")
+        out = {"traj": traj, "state": so, "ref": ref, "err": err}
+        return {k: v.cpu().numpy() for k, v in out.items()} if host else out
 
     def finish_batch(self, tables, path_id, sector, state, sol, prev_x, error_count, advance=True, out=None):
         """Second half of BoundMPC.step for a batch on the device (torch CUDA tensors): accept / reject every solve of

@@ -125,6 +125,17 @@ int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_ta
 int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                     const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
                     const int32_t* error_count, double* traj, double* state_out, void* cuda_stream);
+/* bmpc_post_batch plus the logging branch of compute_return_data (BoundMPC.py:614-755, what `step` returns as ref_data and
+ * err_data when params.real_time is False): per node the reference pose / bounds / bases (`reference_function`,
+ * bound_mpc_functions.py:43-149) and the error terms (`error_function`, :152-202, with the exact rotation error along the
+ * horizon of BoundMPC.py:716-752).  p [batch, np] = the parameter vectors of this step (output of bmpc_prepare_batch).
+ *   ref [batch, N, 55]: p_d(6) dp_d(6) ddp_d(6) dp_normed(3) r_par_bound bound_lower(4) bound_upper(4) e_p_off(2) e_r_off(2)
+ *                       bp1 bp2 br1 br2 v1 v2 v3 (3 each)
+ *   err [batch, N, 33]: e_p de_p e_p_par e_p_orth de_p_par de_p_orth e_r de_r e_r_par e_r_orth1 e_r_orth2 (3 each)  */
+int bmpc_post_log_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                        const int32_t* path_id, const int32_t* sector, const double* state, const double* p, const double* w,
+                        const int32_t* error_count, double* traj, double* state_out, double* ref, double* err, void* cuda_stream);
+
 /* Second half of `BoundMPC.step` as a whole (BoundMPC.py:454-506) for a batch, optionally with the closed-loop advance of
  * bound_mpc_node.py:321-331,362 — the step of an on-device roll-out (with bmpc_prepare_batch and bmpc_solve_batch, no host
  * round trip).  Per instance: the solve is accepted if status == 0 or the summed constraint violation beyond 1e-6 is below

@@ -88,6 +88,22 @@ int emu_post(const bmpc_config* cfg, int batch, const double* tabs, int J, const
   return 0;
 }
 
+// post-processing with the logging branch (serial form of k_post with ref / err)
+int emu_post_log(const bmpc_config* cfg, int batch, const double* tabs, int J, const int32_t* path_id, const int32_t* sector, const double* state,
+                 const double* p, const double* w, const int32_t* ec, double* traj, double* state_out, double* ref, double* err) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  for (int b = 0; b < batch; b++) {
+    const double* tab = tabs + (size_t)path_id[b] * J * PT_ROW;
+    double* T = traj + (size_t)b * C.N * TR_ROW;
+    double* so = state_out + (size_t)b * PS_SIZE;
+    post_instance(C, tab, sector[b], state + (size_t)b * PS_SIZE, w + (size_t)b * C.n, ec[b], T, so);
+    log_instance(C, tab, sector[b], state + (size_t)b * PS_SIZE, p + (size_t)b * C.np, T, ec[b], so + PS_PRREF, ref + (size_t)b * C.N * RF_ROW,
+                 err + (size_t)b * C.N * ER_ROW);
+  }
+  return 0;
+}
+
 // second half of BoundMPC.step + closed-loop advance (k_finish of bmpc_kernels.cu, serial form)
 int emu_finish(const bmpc_config* cfg, int batch, const double* tabs, int J, const int32_t* path_id, const int32_t* sector, const double* state,
                const double* x, const double* g, const int32_t* status, double* prev, int32_t* ec, double* traj, double* state_out, int advance) {

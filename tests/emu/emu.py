@@ -138,3 +138,19 @@ def finish(tabs, path_id, sector, state, x, g, status, prev, ec, advance=True, N
                           _p(g), st.ctypes.data_as(i32p), _p(prev), e.ctypes.data_as(i32p), _p(traj), _p(so), int(advance))
     assert rc == 0
     return traj, so, prev, e
+
+
+def post_log(tabs, path_id, sector, state, p, w, ec, N=10, S=4, dt=0.1):
+    """Serial form of k_post with the logging branch.  Returns traj, next state, ref [B, N, 55], err [B, N, 33]."""
+    tabs = np.ascontiguousarray(tabs, float)
+    state = np.ascontiguousarray(np.atleast_2d(state), float)
+    p = np.ascontiguousarray(np.atleast_2d(p), float); w = np.ascontiguousarray(np.atleast_2d(w), float)
+    B = state.shape[0]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    pid = np.ascontiguousarray(path_id, np.int32); sec = np.ascontiguousarray(sector, np.int32); e = np.ascontiguousarray(ec, np.int32)
+    traj, so, ref, err = np.empty((B, N, 42)), np.empty((B, 76)), np.empty((B, N, 55)), np.empty((B, N, 33))
+    cfg = make_cfg(N, S, dt)
+    rc = lib().emu_post_log(ctypes.byref(cfg), B, _p(tabs), tabs.shape[1], pid.ctypes.data_as(i32p), sec.ctypes.data_as(i32p), _p(state), _p(p),
+                            _p(w), e.ctypes.data_as(i32p), _p(traj), _p(so), _p(ref), _p(err))
+    assert rc == 0
+    return traj, so, ref, err

@@ -10,6 +10,30 @@ from boundmpc_b200 import batches, scenarios
 from boundmpc_b200.bound_mpc import integrate_joint
 from boundmpc_b200.robot_model import RobotModel
 
+RF = {'p': (0, 6), 'dp': (6, 12), 'ddp': (12, 18), 'dp_normed': (18, 21), 'r_par_bound': (21, 22), 'bound_lower': (22, 26),
+      'bound_upper': (26, 30), 'e_p_off': (30, 32), 'e_r_off': (32, 34), 'bp1': (34, 37), 'bp2': (37, 40), 'br1': (40, 43), 'br2': (43, 46),
+      'v1': (46, 49), 'v2': (49, 52), 'v3': (52, 55)}
+ER = ("e_p", "de_p", "e_p_par", "e_p_orth", "de_p_par", "de_p_orth", "e_r", "de_r", "e_r_par", "e_r_orth1", "e_r_orth2")
+
+
+def _compare_log(ref, err, ref_data, err_data):
+    """ref [N, 55], err [N, 33] of the kernel against the mirror's ref_data / err_data (lists per node)."""
+    from boundmpc_b200.lie import exp_so3
+    worst = 0.0
+    for key, (a, b) in RF.items():
+        m = np.array([np.ravel(x) for x in ref_data[key]])
+        k = ref[:len(m), a:b]
+        if key == 'p':       # rotation part: a rotation vector of angle pi has two representations; compare the rotations
+            worst = max(worst, float(np.abs(k[:, :3] - m[:, :3]).max()))
+            worst = max(worst, max(float(np.abs(exp_so3(k[i, 3:]) - exp_so3(m[i, 3:])).max()) for i in range(len(m))))
+        else:
+            worst = max(worst, float(np.abs(k - m).max()))
+    for j, key in enumerate(ER):
+        m = np.array([np.ravel(x) for x in err_data[key]])
+        worst = max(worst, float(np.abs(err[:len(m), 3 * j:3 * j + 3] - m).max()))
+    return worst
+
+
 COLS = {"p": slice(0, 6), "v": slice(6, 12), "a": slice(12, 18), "q": slice(18, 25), "dq": slice(25, 32), "ddq": slice(32, 39)}
 
 
@@ -26,7 +50,7 @@ def _compare(T, traj, M):
 def test_post_matches_host_mirror_along_the_closed_loop(name, steps):
     s = EmuSolver()
     scn = scenarios.experiment1(n=10) if name == "exp1" else scenarios.experiment2(n=10)
-    mpc = batches.make_mpc(scn, s)
+    mpc = batches.make_mpc(scn, s, real_time=False)          # real_time False: step also returns ref_data / err_data
     tab = mpc.ref_path.path_table()[None]
     rm = RobotModel()
     q, dq, ddq, jerk, v = scn['q0'].copy(), np.zeros(7), np.zeros(7), np.zeros(7), np.zeros(6)
@@ -46,9 +70,12 @@ def test_post_matches_host_mirror_along_the_closed_loop(name, steps):
             traj2, _, _ = m2.compute_return_data(np.asarray(sol['x']), True, aux)
             T2, _ = emu.post(tab, [0], [sector], st, np.asarray(sol['x']), [2])
             assert _compare(T2[0], traj2, 8) < 1e-12 and not T2[0][8:].any()
-        traj, _, _, _, _ = mpc.finish(sol, mpc.solver.stats(), aux)
+        traj, ref_data, err_data, _, _ = mpc.finish(sol, mpc.solver.stats(), aux)
         T, so = emu.post(tab, [0], [sector], st, np.asarray(sol['x']), [0])
         assert _compare(T[0], traj, 10) < 1e-12
+        T2, so2, ref, err = emu.post_log(tab, [0], [sector], st, params, np.asarray(sol['x']), [0])      # with the logging branch
+        assert np.array_equal(T2, T) and np.array_equal(so2, so)
+        assert _compare_log(ref[0], err[0], ref_data, err_data) < 1e-11
         ref = np.concatenate(([mpc.phi_current[0], mpc.dphi_current[0], mpc.ddphi_current[0], mpc.dddphi_current[0]], mpc.pr_ref, mpc.iw_ref))
         assert np.abs(so[0][40:50] - ref).max() < 1e-12                      # path-parameter state, pr_ref, iw_ref of the next step
         jm = np.concatenate((jerk[:, None], traj['dddq'][:, :2]), axis=1)
@@ -127,6 +154,16 @@ def test_gpu_post_matches_host_build():
          dict(tables=D["tables"], path_id=D["path_id"], sector=D["sector_out"], state=D["state"], w=w, ec=ec).items()}
     rd = s.post_batch(t["tables"], t["path_id"], t["sector"], t["state"], t["w"], t["ec"])
     assert np.array_equal(rd["traj"].cpu().numpy(), r["traj"]) and np.array_equal(rd["state"].cpu().numpy(), r["state"])
+    # logging branch: reference data and error terms
+    _, _, ref_e, err_e = emu.post_log(D["tables"], D["path_id"], D["sector_out"], D["state"], D["p"], w, ec)
+    rl = s.post_log_batch(D["tables"], D["path_id"], D["sector_out"], D["state"], D["p"], w, ec)
+    assert np.array_equal(rl["traj"], r["traj"])
+    assert np.abs(rl["err"] - err_e).max() < 1e-10
+    rot = np.abs(rl["ref"][:, :, 3:6] - ref_e[:, :, 3:6]).max(axis=2)        # (sign of a rotation vector of angle pi)
+    flip = np.abs(rl["ref"][:, :, 3:6] + ref_e[:, :, 3:6]).max(axis=2)
+    assert (np.minimum(rot, flip) < 1e-10).all()
+    mask = np.ones(55, bool); mask[3:6] = False
+    assert np.abs(rl["ref"][:, :, mask] - ref_e[:, :, mask]).max() < 1e-10
 
 
 @pytest.mark.gpu
