@@ -270,6 +270,7 @@ class BoundMPC:
         st[57] = self.phi_max[0]
         st[58:73] = self.weights
         st[73] = 0.0 if self.prev_solution is None else 1.0
+        st[74] = 1.0 if self.updated else 0.0
         prev = np.zeros(self.N * self.nr_x) if self.prev_solution is None else np.asarray(self.prev_solution, float).ravel()
         return st, int(self.ref_path.sector), prev
 

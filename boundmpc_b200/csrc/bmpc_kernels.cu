@@ -207,15 +207,21 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(const __grid_constant_
   const size_t n = C.n;
   if (b < batch) {
     const double* st = io.state + (size_t)b * PS_SIZE;
-    io.sector[b] = prepare_params(C.L, io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW, io.J, io.sector[b], st, io.p + (size_t)b * C.np);
+    const double* tab = io.tabs + (size_t)io.path_id[b] * io.J * PT_ROW;
+    const int sec = prepare_params(C.L, tab, io.J, io.sector[b], st, io.p + (size_t)b * C.np);
+    io.sector[b] = sec;
     rev[threadIdx.x] = st[PS_HASPREV] != 0.0 && warm_reverse(st, io.prev + b * n);
+    if (st[PS_HASPREV] != 0.0 && st[PS_UPDATED] != 0.0) {          // after a path update: re-projected warm start, written by its owner
+      warm_start_updated_at(C, tab, sec, st, io.prev + b * n, io.x0 + b * n);
+      rev[threadIdx.x] = 2;
+    }
   }
   __syncthreads();
   const int cnt = batch - base < PREP_THREADS ? batch - base : PREP_THREADS;
   for (size_t idx = threadIdx.x; idx < (size_t)cnt * n; idx += PREP_THREADS) {
     const int i = (int)(idx / n), e = (int)(idx - (size_t)i * n), k = e / NX, a = e - NX * k;
     const size_t bi = (size_t)(base + i);
-    io.x0[bi * n + e] = warm_start_value(C.N, io.state + bi * PS_SIZE, io.prev + bi * n, rev[i] != 0, k, a);
+    if (rev[i] != 2) io.x0[bi * n + e] = warm_start_value(C.N, io.state + bi * PS_SIZE, io.prev + bi * n, rev[i] != 0, k, a);
   }
 }
 
@@ -240,6 +246,19 @@ __global__ void __launch_bounds__(PREP_THREADS) k_post(const __grid_constant__ C
   if (io.ref)
     log_instance(C, tab, io.sector[b], st, io.p + (size_t)b * C.np, traj, ec, so + PS_PRREF, io.ref + (size_t)b * C.N * RF_ROW,
                  io.err + (size_t)b * C.N * ER_ROW);
+}
+
+// k_update: BoundMPC.update for a batch (bmpc_post.cuh update_state): new path, projected path-parameter state, restarted
+// rotation reference, window back at the start of the path.
+struct UpdateIO { const double* tabs; int J; const double* phimax; const int32_t* new_path; const double* cart; double* state; int32_t* sector; int32_t* path_id; };
+__global__ void __launch_bounds__(PREP_THREADS) k_update(int batch, UpdateIO io) {
+  const int b = blockIdx.x * PREP_THREADS + threadIdx.x;
+  if (b >= batch) return;
+  const int pth = io.new_path[b];
+  if (pth < 0) return;                                            // this controller keeps its path
+  update_state(io.tabs + (size_t)pth * io.J * PT_ROW, io.phimax[pth], io.cart + (size_t)b * 24, io.state + (size_t)b * PS_SIZE);
+  io.sector[b] = 0;
+  io.path_id[b] = pth;
 }
 
 // k_finish: second half of BoundMPC.step for a batch + closed-loop advance (bmpc_post.cuh).  Phase 1: one thread per instance
@@ -607,6 +626,20 @@ int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, in
   CU(cudaSetDevice(h->device));
   PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out, nullptr, nullptr, nullptr};
   k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_update_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const double* path_phi_max,
+                      const int32_t* new_path, const double* cart, double* state, int32_t* sector, int32_t* path_id, void* cuda_stream) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_update_batch: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < 1 || !path_tables || !path_phi_max || !new_path || !cart || !state || !sector || !path_id)
+    return fail(BMPC_E_INVALID, "bmpc_update_batch: invalid argument");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  UpdateIO io{path_tables, path_rows, path_phi_max, new_path, cart, state, sector, path_id};
+  k_update<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(batch, io);
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

@@ -258,6 +258,104 @@ BMPC_DEV void log_instance(const Config& C, const double* tab, int sector, const
   }
 }
 
+// ---- replanning: `BoundMPC.update` (BoundMPC.py:163-217) and the re-projected warm start (:335-369)
+// J_v(q) xa and dJ_v(q, dq) xb (linear rows of the geometric Jacobian and of its time derivative along dq)
+BMPC_DEV void rm_lin(const double* q, const double* dq, const double* xa, const double* xb, double* Jxa, double* dJxb) {
+  double z[7][3], o[7][3], p[3], R[9];
+  rm_chain(q, z, o, p, R);
+  double Om[8][3] = {{0, 0, 0}};
+  for (int i = 0; i < 7; i++) for (int a = 0; a < 3; a++) Om[i + 1][a] = Om[i][a] + dq[i] * z[i][a];
+  for (int a = 0; a < 3; a++) { Jxa[a] = 0.0; dJxb[a] = 0.0; }
+  double tail[3] = {0, 0, 0};
+  for (int i = 6; i >= 0; i--) {
+    double r[3], zr[3], zd[3], rd[3], c1[3], c2[3], t2[3];
+    for (int a = 0; a < 3; a++) r[a] = p[a] - o[i][a];
+    cross3(z[i], r, zr);
+    cross3(Om[i], z[i], zd);
+    for (int a = 0; a < 3; a++) tail[a] += dq[i] * zr[a];
+    cross3(Om[i], r, t2);
+    for (int a = 0; a < 3; a++) rd[a] = tail[a] + t2[a];
+    cross3(zd, r, c1);
+    cross3(z[i], rd, c2);
+    for (int a = 0; a < 3; a++) { Jxa[a] += zr[a] * xa[i]; dJxb[a] += (c1[a] + c2[a]) * xb[i]; }
+  }
+}
+
+// Warm start after a path update: the previous solution (after the "reversing integrated omega" repair, not shifted) with
+// its path-parameter entries re-projected on the first segment of the new path; Cartesian acceleration / jerk of the
+// previous trajectory as in compute_return_data (BoundMPC.py:563-571: J ddq + dJ dq and J u + dJ ddq + ddJ dq with the
+// central-difference ddJ of the host model).  `row0` = first window row of the new path, `ps0`, `ps1` = phi_switch[0], [1].
+BMPC_DEV void warm_start_updated(const Config& C, const double* st, const double* prev, bool reverse, const double* row0, double ps0,
+                                 double ps1, double* x0) {
+  const int N = C.N;
+  const double* t = row0 + PT_DPN;
+  const double* pr = row0 + PT_P;
+  for (int i = 0; i < N; i++) {
+    const double* w = prev + NX * i;
+    double* o = x0 + NX * i;
+    for (int a = 0; a < NX; a++) o[a] = w[a];
+    if (reverse) {
+      const int r = i < N - 1 ? i : N - 2;
+      for (int a = 0; a < 3; a++) o[oPROT + a] = st[PS_P0 + 3 + a] + (prev[NX * (r + 1) + oPROT + a] - prev[oPROT + a]);
+    }
+    const double d[3] = {w[oPPOS] - pr[0], w[oPPOS + 1] - pr[1], w[oPPOS + 2] - pr[2]};
+    const double phik = ps0 + dot3(d, t);
+    if (phik > ps1 - 0.01) { o[oPHI] = ps1 - 0.01; o[oDPHI] = 0.0; o[oDDPHI] = 0.0; }
+    else if (phik < 0) {
+      for (int j = 0; j < 7; j++) o[oQ + j] = st[PS_Q + j];
+      for (int a = 0; a < 6; a++) o[oPPOS + a] = st[PS_P0 + a];
+      for (int a = 0; a < 4; a++) o[oVLIN + a] = 0.0;                  // (entries 35..38, as the reference writes them)
+      o[oPHI] = 0.0; o[oDPHI] = 0.0; o[oDDPHI] = 0.0;
+    } else {
+      const double* q = w + oQ;
+      const double* dq = w + oDQ;
+      const double* ddq = w + oDDQ;
+      double Jddq[3], dJdq[3], Ju[3], dJddq[3], up[3], um[3], dummy[3];
+      rm_lin(q, dq, ddq, dq, Jddq, dJdq);
+      rm_lin(q, dq, w + oU, ddq, Ju, dJddq);
+      const double eps = 1e-6;
+      double qp[7], qm[7], dqp[7], dqm[7];
+      for (int j = 0; j < 7; j++) {
+        qp[j] = q[j] + eps * dq[j] + 0.5 * eps * eps * ddq[j]; qm[j] = q[j] - eps * dq[j] + 0.5 * eps * eps * ddq[j];
+        dqp[j] = dq[j] + eps * ddq[j]; dqm[j] = dq[j] - eps * ddq[j];
+      }
+      rm_lin(qp, dqp, dq, dq, dummy, up);
+      rm_lin(qm, dqm, dq, dq, dummy, um);
+      double acc[3], jrk[3];
+      for (int a = 0; a < 3; a++) { acc[a] = Jddq[a] + dJdq[a]; jrk[a] = Ju[a] + dJddq[a] + (up[a] - um[a]) / (2 * eps); }
+      o[oPHI] = phik;
+      o[oDPHI] = dot3(w + oVLIN, t);
+      o[oDDPHI] = dot3(acc, t);
+      o[oUPHI] = dot3(jrk, t);
+    }
+  }
+}
+
+// window rows / switching points the re-projection needs, for the (already slid) window position `sector`
+BMPC_DEV void warm_start_updated_at(const Config& C, const double* tab, int sector, const double* st, const double* prev, double* x0) {
+  const double* row0 = tab + (size_t)sector * PT_ROW;
+  const double ps0 = sector == 0 ? 0.0 : row0[PT_CUM - PT_ROW], ps1 = row0[PT_CUM];
+  warm_start_updated(C, st, prev, warm_reverse(st, prev), row0, ps0, ps1, x0);
+}
+
+// BoundMPC.update for one controller: the measured Cartesian state cart = (p0(6), v(6), a(6), jerk(6)) projected on the
+// first segment of the new path `tab` (row 0), rotation reference restarted at the first via point.
+BMPC_DEV void update_state(const double* tab, double path_phimax, const double* cart, double* st) {
+  const double* row0 = tab;
+  const double* t = row0 + PT_DPN;
+  const double d[3] = {cart[0] - row0[PT_P], cart[1] - row0[PT_P + 1], cart[2] - row0[PT_P + 2]};
+  const double phi = dot3(d, t);
+  st[PS_PHI] = phi;
+  st[PS_PHI + 1] = dot3(cart + 6, t);
+  st[PS_PHI + 2] = dot3(cart + 12, t);
+  st[PS_PHI + 3] = dot3(cart + 18, t);
+  double prn[3];
+  integrate_rot_ref(row0 + PT_LOGR, row0 + PT_DR, 0.0, phi, prn);
+  for (int a = 0; a < 3; a++) { st[PS_PRREF + a] = prn[a]; st[PS_IWREF + a] = row0[PT_IW + a] + phi * row0[PT_DR + a]; }
+  st[PS_PHIMAX] = path_phimax - 0.0001;
+  st[PS_UPDATED] = 1.0;
+}
+
 // ---- second half of `BoundMPC.step` as a whole (BoundMPC.py:454-506 + compute_return_data) and the closed-loop advance of
 // bound_mpc_node.py:321-331,362.  Decision per instance:
 //   success = solver success or summed constraint violation beyond 1e-6 below 1e-4 (BoundMPC.py:461-465)

@@ -13,7 +13,8 @@
 //   * quartic error-bound coefficients: `compute_error_bounds` (BoundMPC.py:219-265) +
 //     `compute_bound_params` (mpc_utils_casadi.py:130-137),
 //   * weight / path-parameter clamps of BoundMPC.py:397-414 and the parameter order of :416-443.
-// The re-projection branch after `update()` (BoundMPC.py:335-369, replanning) is not covered.
+// The re-projection branch after `update()` (BoundMPC.py:335-369, replanning) needs the kinematic model: bmpc_post.cuh
+// (warm_start_updated), called by k_prepare for states with the `updated` flag.
 // One thread builds one instance (the work is a few hundred scalar operations on 3-vectors); the functions
 // are plain host/device code so that tests/emu runs the same source on the CPU.
 #pragma once
@@ -49,6 +50,8 @@ enum {
   PS_PHIMAX = 57,    // [1] BoundMPC.phi_max = path length - 1e-4
   PS_W = 58,         // [15] weights
   PS_HASPREV = 73,   // [1] != 0: prev_x holds the previous solution (warm start), else cold start
+  PS_UPDATED = 74,   // [1] != 0: the path has been replaced (BoundMPC.update): the warm start is re-projected on the new path
+                     //     (BoundMPC.py:335-369) instead of shifted; like the reference's flag it is never reset
   PS_SIZE = 76
 };
 

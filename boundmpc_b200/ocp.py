@@ -272,6 +272,17 @@ class BatchSolver:
         out = {"traj": traj, "state": so, "ref": ref, "err": err}
         return {k: v.cpu().numpy() for k, v in out.items()} if host else out
 
+    def update_batch(self, tables, path_phi_max, new_path, cart, state, sector, path_id):
+        """BoundMPC.update for a batch on the device (torch CUDA tensors): controllers with new_path[b] >= 0 switch to that
+        path; state [B, 76], sector [B], path_id [B] are updated in place.  cart [B, 24] = measured pose, velocity,
+        acceleration, jerk (Cartesian)."""
+        import torch
+        V = ctypes.c_void_p
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        _cabi.check(self._lib.bmpc_update_batch(self._h, int(state.shape[0]), V(tables.data_ptr()), int(tables.shape[0]), int(tables.shape[1]),
+                                                V(path_phi_max.data_ptr()), V(new_path.data_ptr()), V(cart.data_ptr()), V(state.data_ptr()),
+                                                V(sector.data_ptr()), V(path_id.data_ptr()), V(stream)), "bmpc_update_batch")
+
     def finish_batch(self, tables, path_id, sector, state, sol, prev_x, error_count, advance=True, out=None):
         """Second half of BoundMPC.step for a batch on the device (torch CUDA tensors): accept / reject every solve of
         `sol` (dict of solve_batch), keep the previous solution where rejected, post-process and (advance=True) move the

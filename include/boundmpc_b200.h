@@ -101,7 +101,7 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
  *                                         iw_ref, x_phi_d, bound factors, phi_max, weights, has_prev)
  *   prev_x      [batch, n]                previous solution (read when has_prev != 0)
  *   x0 [batch, n], p [batch, np]          outputs
- * The re-projection of the warm start after a path update (BoundMPC.py:335-369) is not covered. */
+ * States with state[74] != 0 (set by bmpc_update_batch) get the re-projected warm start of BoundMPC.py:335-369. */
 int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                        const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x,
                        double* x0, double* p, void* cuda_stream);
@@ -125,6 +125,16 @@ int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_ta
 int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                     const int32_t* path_id, const int32_t* sector, const double* state, const double* w,
                     const int32_t* error_count, double* traj, double* state_out, void* cuda_stream);
+/* Replanning: replaces `BoundMPC.update` (BoundMPC.py:163-217) for a batch.  Controller b with new_path[b] >= 0 moves to
+ * that path (tables as for bmpc_prepare_batch, path_phi_max [n_paths] = ReferencePath.phi_max): its path-parameter state is
+ * the projection of the measured Cartesian state cart [batch, 24] = (pose(6), velocity(6), acceleration(6), jerk(6)) on the
+ * first segment, the rotation reference restarts at the first via point, the window at the start of the path, and
+ * state[74] (updated) is set: from then on bmpc_prepare_batch re-projects the previous solution on the new path
+ * (BoundMPC.py:335-369) instead of shifting it.  new_path[b] < 0: controller b is left alone.  DEVICE pointers. */
+int bmpc_update_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                      const double* path_phi_max, const int32_t* new_path, const double* cart, double* state,
+                      int32_t* sector, int32_t* path_id, void* cuda_stream);
+
 /* bmpc_post_batch plus the logging branch of compute_return_data (BoundMPC.py:614-755, what `step` returns as ref_data and
  * err_data when params.real_time is False): per node the reference pose / bounds / bases (`reference_function`,
  * bound_mpc_functions.py:43-149) and the error terms (`error_function`, :152-202, with the exact rotation error along the

@@ -71,9 +71,27 @@ int emu_prepare(int N, int S, int batch, const double* tabs, int J, const int32_
                 const double* prev, double* x0, double* p) {
   const PLayout L = make_layout(S);
   if (S > PREP_SMAX) return -1;
-  for (int b = 0; b < batch; b++)
-    sector[b] = prepare_instance(L, N, tabs + (size_t)path_id[b] * J * PT_ROW, J, sector[b], state + (size_t)b * PS_SIZE,
-                                 prev + (size_t)b * NX * N, x0 + (size_t)b * NX * N, p + (size_t)b * L.np);
+  Config C;                      // (only N is read by the re-projected warm start)
+  C.N = N;
+  for (int b = 0; b < batch; b++) {
+    const double* tab = tabs + (size_t)path_id[b] * J * PT_ROW;
+    const double* st = state + (size_t)b * PS_SIZE;
+    sector[b] = prepare_instance(L, N, tab, J, sector[b], st, prev + (size_t)b * NX * N, x0 + (size_t)b * NX * N, p + (size_t)b * L.np);
+    if (st[PS_HASPREV] != 0.0 && st[PS_UPDATED] != 0.0)          // as in k_prepare
+      warm_start_updated_at(C, tab, sector[b], st, prev + (size_t)b * NX * N, x0 + (size_t)b * NX * N);
+  }
+  return 0;
+}
+
+// BoundMPC.update (k_update)
+int emu_update(int batch, const double* tabs, int J, const double* phimax, const int32_t* new_path, const double* cart, double* state,
+               int32_t* sector, int32_t* path_id) {
+  for (int b = 0; b < batch; b++) {
+    if (new_path[b] < 0) continue;
+    update_state(tabs + (size_t)new_path[b] * J * PT_ROW, phimax[new_path[b]], cart + (size_t)b * 24, state + (size_t)b * PS_SIZE);
+    sector[b] = 0;
+    path_id[b] = new_path[b];
+  }
   return 0;
 }
 

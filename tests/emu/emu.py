@@ -154,3 +154,16 @@ def post_log(tabs, path_id, sector, state, p, w, ec, N=10, S=4, dt=0.1):
                             _p(w), e.ctypes.data_as(i32p), _p(traj), _p(so), _p(ref), _p(err))
     assert rc == 0
     return traj, so, ref, err
+
+
+def update(tabs, phimax, new_path, cart, state, sector, path_id):
+    """Serial form of k_update.  Returns updated copies of state, sector, path_id."""
+    tabs = np.ascontiguousarray(tabs, float); phimax = np.ascontiguousarray(phimax, float)
+    cart = np.ascontiguousarray(np.atleast_2d(cart), float)
+    state = np.ascontiguousarray(np.atleast_2d(state), float).copy()
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    npth = np.ascontiguousarray(new_path, np.int32); sec = np.ascontiguousarray(sector, np.int32).copy(); pid = np.ascontiguousarray(path_id, np.int32).copy()
+    rc = lib().emu_update(state.shape[0], _p(tabs), tabs.shape[1], _p(phimax), npth.ctypes.data_as(i32p), _p(cart), _p(state),
+                          sec.ctypes.data_as(i32p), pid.ctypes.data_as(i32p))
+    assert rc == 0
+    return state, sec, pid

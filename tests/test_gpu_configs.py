@@ -80,3 +80,28 @@ def test_bench_size_batch_properties():
     assert torch.equal(b["x"], a["x"][perm])          # same instance -> bitwise same solution on any CTA
     assert torch.equal(b["iters"], a["iters"][perm])
     assert torch.equal(b["lam_g"], a["lam_g"][perm])
+
+
+def test_bench_batch_sample_against_oracle():
+    """configs[4] shard: every 64th instance of the 8,192-instance bench batch solved by the CPU oracle from the same
+    inputs — same termination status, joint trajectory within 1e-6 relative, objective within 1e-7 relative, same
+    active set (north-star parity criteria); a few instances have two local solutions that rounding decides between."""
+    from boundmpc_b200 import batches
+    from oracle import oracle as O
+    from tests.util import active_set
+    s = _solver(10)
+    x0, p = batches.make_batch(s, ("exp1", "exp2"), 0, 8192, bound_scale=True)
+    idx = np.arange(0, 8192, 64)
+    r = s.solve_batch(x0[idx], p[idx])
+    same = 0
+    for j, i in enumerate(idx):
+        ro = O.solve(x0[i], p[i], tol=s.tol)
+        assert ro["status"] == r["status"][j]
+        if ro["status"] != 0:
+            continue
+        if rel_q_error(r["x"][j], ro["x"]) < 1e-6:
+            same += 1
+            assert abs(r["f"][j] - ro["f"]) < 1e-7 * abs(ro["f"])
+            assert active_set({"x": r["x"][j], "g": r["g"][j]}) == active_set(ro)
+            assert abs(int(r["iters"][j]) - ro["iters"]) <= 2
+    assert same >= len(idx) - 2
