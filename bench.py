@@ -201,7 +201,7 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # (keeps NCCL's version banner off stdout: one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # (NCCL's version banner off stdout: one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peak_dfma = solver.fp64_peak(0)
@@ -255,9 +255,13 @@ def main():
     kkt = out["kkt"].cpu().numpy()
     ok = int((status == 0).sum())
     cnt = torch.tensor([ok, int(iters.sum()), per_gpu], dtype=torch.float64, device=dev)
+    rank_stats = torch.tensor([k_ms, float(iters.max()), float(iters.mean()), float(ok)], dtype=torch.float64, device=dev)
+    all_stats = [rank_stats.clone() for _ in range(max(1, world))]
     if world > 1:
         dist.all_reduce(cnt)
+        dist.all_gather(all_stats, rank_stats)
         assert int((gathered["status"] == 0).sum().item()) == int(cnt[0].item())
+    per_rank = [{"kernel_ms": float(t_[0]), "iters_max": int(t_[1]), "iters_mean": float(t_[2]), "success": int(t_[3])} for t_ in all_stats]
 
     # ---- end to end through the host-pointer C-ABI entry, pinned host buffers
     def pinned(shape, dtype=torch.float64):
@@ -432,6 +436,7 @@ def main():
             "clocks": ck,
             "solver": {"success": int(cnt[0].item()), "instances": total, "iters_mean": sum_iters / total,
                        "iters_max_rank0": int(iters.max()), "kkt_max_rank0": float(kkt[status == 0].max()) if ok else None,
+                       "per_rank": per_rank,
                        "perturbation_scale_hist_rank0": {str(v): int((scale == v).sum()) for v in np.unique(scale)},
                        "input_generation_s": t_gen},
             "builder": builder,
