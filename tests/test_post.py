@@ -197,3 +197,21 @@ def test_gpu_rollout_follows_the_host_mirror_closed_loop():
         assert np.abs(q[:, k] - refs[k][0]).max() < 1e-6
         it = np.array(out["iters"][:, k].cpu().tolist()) - np.array(refs[k][1])      # (inputs differ in the last bits)
         assert (it == 0).mean() >= 0.9 and np.abs(it).max() <= 2
+
+
+def test_finish_gives_up_after_n_rejected_solves():
+    """BoundMPC.py:504-506: with error_count reaching N nothing is returned; the kernel writes a zero trajectory, leaves the
+    controller state alone and keeps the previous solution."""
+    s = EmuSolver()
+    D = batches.make_builder_batch(s, ("exp2",), 2, 1)
+    assert D["state"][0, 73] == 1.0
+    g = np.zeros((1, 430)); g[0, 5] = 1.0                      # a violated equality row
+    traj, so, prev, ec = emu.finish(D["tables"], D["path_id"], D["sector_out"], D["state"], D["x0"], g, [1], D["prev"], [9])
+    assert ec[0] == 10 and not traj.any()
+    assert np.array_equal(so[0], D["state"][0]) and np.array_equal(prev, D["prev"])
+    traj, so, prev, ec = emu.finish(D["tables"], D["path_id"], D["sector_out"], D["state"], D["x0"], g, [1], D["prev"], [3])
+    assert ec[0] == 4 and traj[0, :6].any() and not traj[0, 6:].any()
+    # without a previous solution the rejected point is used anyway and no previous solution is recorded (BoundMPC.py:480-486)
+    st = D["state"].copy(); st[0, 73] = 0.0
+    traj, so, prev, ec = emu.finish(D["tables"], D["path_id"], D["sector_out"], st, D["x0"], g, [1], D["prev"], [0])
+    assert ec[0] == 0 and so[0, 73] == 0.0 and np.array_equal(prev, D["prev"]) and traj[0, 9].any()
