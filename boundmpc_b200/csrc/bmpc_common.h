@@ -307,6 +307,19 @@ BMPC_DEV void cp_async_wait() {
 #endif
 }
 
+// cp.async groups: copies issued since the last commit form a group; wait_group1 returns when all groups but the
+// most recent one have landed
+BMPC_DEV void cp_async_commit() {
+#ifndef BMPC_HOST_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+BMPC_DEV void cp_async_wait_group1() {
+#ifndef BMPC_HOST_EMU
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+
 // one copy each of the transcendental routines
 BMPC_NOINLINE double bmpc_log(double v) { return log(v); }
 BMPC_NOINLINE double bmpc_exp(double v) { return exp(v); }

@@ -131,22 +131,60 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     eval_full(cx, C, W, p, W.x);
     // ---- optimality error (Ipopt's E_mu), constraint violation theta
     double rv[8] = {0, 0, 0, 0, 1e300, 0, 0, 0};   // dinf, pinf, ysum, zsum, szmin, szmax, theta, f
-    PAR_FOR(i, n) {
-      const int k = i / NX, a = i - NX * k;
-      double r = W.gradf[i] - W.zL[i] + W.zU[i];
-      const double* GKk = W.rec + (size_t)k * R_SIZE + R_GK;
-      if (a < 8) r += GT_tab(S, GKk, W.y + NE * k, NX + a);
-      else r -= W.y[NE * k + a - 8];
-      if (k + 1 < N) r += GT_tab(S, GKk + R_SIZE, W.y + NE * (k + 1), a);
-      const int ya = (a >= oPPOS && a < oPPOS + 6) ? a - oPPOS : (a == oPHI ? 6 : (a == oDPHI ? 7 : -1));
-      if (ya >= 0) {
-        const double* JD = W.rec + (size_t)k * R_SIZE + R_JD;
-        for (int q = 0; q < ND; q++) r += JD[q * 8 + ya] * W.zs[ND * k + q];
+    // dual infeasibility of variable (k, a): grad f - z_L + z_U + [G^T y]_(k, a) + J_d^T z_s.  The variables are taken
+    // class by class (u columns, y columns, the rest), each class a straight-line body whose reads of the global stage
+    // records are all issued before the first product: one L2 round trip per item instead of one per branch.
+    {
+      auto gcol = [&](const double* g, const double* v, int col) {   // (G^T v)[col], kinematic rows in registers
+        double s0 = 0.0;
+#pragma unroll
+        for (int r = 0; r < NK; r++) s0 += g[r] * v[rKIN + r];
+#pragma unroll
+        for (int t = 0; t < 3; t++) s0 += S.tcc[3 * col + t] * v[S.tcr[3 * col + t]];
+        return s0;
+      };
+      auto finish = [&](int i, int a, double r) {
+        rv[0] = fmax(rv[0], fabs(r));
+        const double l = C.lb[a], u = C.ub[a];
+        if (l > -1e300) { const double pr = (W.x[i] - l) * W.zL[i]; rv[3] += W.zL[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
+        if (u < 1e300) { const double pr = (u - W.x[i]) * W.zU[i]; rv[3] += W.zU[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
+      };
+      PAR_FOR(it, 16 * N) {      // u columns (own stage: columns 44..51 of G_k) and y columns (interval-row gradients)
+        const bool isu = it < 8 * N;
+        const int q = isu ? it : it - 8 * N, k = q >> 3, a = isu ? (q & 7) : yrow(q & 7), i = NX * k + a;
+        const bool hn = k + 1 < N;
+        const double* GKk = W.rec + (size_t)k * R_SIZE + R_GK;
+        const double* g1p = isu ? GKk + NX + a : W.rec + (size_t)k * R_SIZE + R_JD + (q & 7);
+        const int g1s = isu ? NZ : 8;
+        const double* g2p = GKk + (hn ? R_SIZE : 0) + a;
+        double g1[NK], g2[NK];
+#pragma unroll
+        for (int r = 0; r < NK; r++) { g1[r] = g1p[r * g1s]; g2[r] = g2p[r * NZ]; }
+        double r = W.gradf[i] - W.zL[i] + W.zU[i];
+        if (isu) r += gcol(g1, W.y + NE * k, NX + a);
+        else {
+          r -= W.y[NE * k + a - 8];
+          double s0 = 0.0;
+#pragma unroll
+          for (int t = 0; t < ND; t++) s0 += g1[t] * W.zs[ND * k + t];
+          r += s0;
+        }
+        const double s2 = gcol(g2, W.y + NE * (hn ? k + 1 : k), a);
+        if (hn) r += s2;
+        finish(i, a, r);
       }
-      rv[0] = fmax(rv[0], fabs(r));
-      const double l = C.lb[a], u = C.ub[a];
-      if (l > -1e300) { const double pr = (W.x[i] - l) * W.zL[i]; rv[3] += W.zL[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
-      if (u < 1e300) { const double pr = (u - W.x[i]) * W.zU[i]; rv[3] += W.zU[i]; rv[4] = fmin(rv[4], pr); rv[5] = fmax(rv[5], pr); }
+      PAR_FOR(it, 28 * N) {      // q, dq, ddq, v, ddphi
+        const int k = it / 28, j = it - 28 * k, a = j < 21 ? 8 + j : (j < 27 ? oVLIN + j - 21 : oDDPHI), i = NX * k + a;
+        const bool hn = k + 1 < N;
+        const double* g2p = W.rec + (size_t)(hn ? k + 1 : k) * R_SIZE + R_GK + a;
+        double g2[NK];
+#pragma unroll
+        for (int r = 0; r < NK; r++) g2[r] = g2p[r * NZ];
+        double r = W.gradf[i] - W.zL[i] + W.zU[i] - W.y[NE * k + a - 8];
+        const double s2 = gcol(g2, W.y + NE * (hn ? k + 1 : k), a);
+        if (hn) r += s2;
+        finish(i, a, r);
+      }
     }
     PAR_FOR(i, ne) { const double cv = fabs(W.c[i]); rv[1] = fmax(rv[1], cv); rv[2] += fabs(W.y[i]); rv[6] += cv; }
     PAR_FOR(i, nd) {

@@ -167,15 +167,16 @@ BMPC_NOINLINE void fk_chain(double* f) {
   }
 }
 
-BMPC_DEV void phase_fk(const Ctx cx, const Config& C, const Work& W) {
-  ROLE_FOR(it, 2 * C.N, 0, 1) fk_chain(W.fk + (size_t)it * F_SIZE);
+BMPC_DEV void phase_fk(const Ctx cx, const Config& C, const Work& W, int w = 0) {
+  ROLE_FOR(it, 2 * C.N, w, w + 1) fk_chain(W.fk + (size_t)it * F_SIZE);
 }
 
 // Phase 3a: kinematic residual rows 21..32 (casadi_ocp_formulation.py:284-291,
 // bound_mpc_functions.py:262-282: p_pos = fk_pos(q_n), v = [velocity_ee; omega_ee](q_n, dq_n),
 // trapezoidal integration of omega into p_rot)
-BMPC_DEV void phase_kin_residual(const Ctx cx, const Config& C, const Work& W, const double* x, double* c) {
-  PAR_FOR(it, C.N * 3) {
+// (the kinematic phases take a warp range [w0, w1): eval_full runs them next to the path terms)
+BMPC_DEV void phase_kin_residual(const Ctx cx, const Config& C, const Work& W, const double* x, double* c, int w0, int w1) {
+  ROLE_FOR(it, C.N * 3, w0, w1) {
     const int k = it / 3, i = it - 3 * k;
     const double* wp = prev_block(W, x, k);
     const double* w = x + NX * k;
@@ -459,8 +460,8 @@ BMPC_DEV void phase_path_blocks(const Ctx cx, const Config& C, const Work& W, co
 // (integrated state) the scalar is
 //   Phi = lam_p . fk_pos + lam_v . (Jv dq) + (lam_w + h/2 lam_rot) . (Jw dq)
 // and for ch = 2k+1 (stage variables) it is  h/2 lam_rot . Jw(q_k) dq_k  (SURVEY App. A.7).
-BMPC_DEV void phase_kin_hessian(const Ctx cx, const Config& C, const Work& W) {
-  PAR_FOR(it, 2 * C.N * 49) {
+BMPC_DEV void phase_kin_hessian(const Ctx cx, const Config& C, const Work& W, int w0, int w1) {
+  ROLE_FOR(it, 2 * C.N * 49, w0, w1) {
     const int ch = it / 49, ij = it - 49 * ch, i = ij / 7, j = ij - 7 * i;
     const int k = ch >> 1, which = ch & 1;
     const double* f = W.fk + (size_t)ch * F_SIZE;
@@ -515,8 +516,8 @@ BMPC_DEV void phase_kin_jacobian_init(const Ctx cx, const Config& C, const Work&
     if (col >= oPROT && col < oPROT + 3) GK[(3 + col - oPROT) * NZ + col] = 1.0;
   }
 }
-BMPC_DEV void phase_kin_jacobian(const Ctx cx, const Config& C, const Work& W) {
-  PAR_FOR(it, C.N * 7) {
+BMPC_DEV void phase_kin_jacobian(const Ctx cx, const Config& C, const Work& W, int w0, int w1) {
+  ROLE_FOR(it, C.N * 7, w0, w1) {
     const int k = it / 7, j = it - 7 * k;
     const double* f0 = W.fk + (size_t)(2 * k) * F_SIZE;
     const double* f1 = f0 + F_SIZE;
@@ -587,25 +588,40 @@ BMPC_NOINLINE void eval_values(const Ctx cx, const Config& C, const Work& W, con
   phase_path(cx, C, W, p, x, d, nullptr, 0, 1);
   BMPC_SYNC();
   BMPC_TMARK(4);
-  phase_kin_residual(cx, C, W, x, c);
+  phase_kin_residual(cx, C, W, x, c, 0, ctx_nwarps(cx));
   BMPC_SYNC();
   BMPC_TMARK(5);
 }
 
+// The path terms with derivatives are by far the longest serial piece of an evaluation (one lane per stage, several
+// times the kinematic chains).  Everything that needs the chains only - kinematic residual rows, curvature matrices,
+// Jacobian rows - therefore runs NEXT to them: warp 0 has the path terms, warp 1 the chains, and warps 1 .. nw-1 go on
+// with the kinematic phases after a barrier of their own (named barrier 1).
+BMPC_DEV void role_barrier(const Ctx cx, int w0, int w1) {
+#ifndef BMPC_HOST_EMU
+  if (in_role(cx, w0, w1)) asm volatile("bar.sync 1, %0;" ::"r"(32 * (w1 - w0)) : "memory");
+#else
+  (void)cx; (void)w0; (void)w1;
+#endif
+}
 BMPC_NOINLINE void eval_full(const Ctx cx, const Config& C, const Work& W, const double* p, const double* x) {
+  const int nw = ctx_nwarps(cx);
   phase_integrate(cx, C, W, x, W.c);
   BMPC_SYNC();
   BMPC_TMARK(0);
-  phase_fk(cx, C, W);
-  phase_path(cx, C, W, p, x, W.d, nullptr, 1, 1);
+#ifdef BMPC_HOST_EMU
+  const int k0 = 0;
+#else
+  const int k0 = 1;
+#endif
+  phase_path(cx, C, W, p, x, W.d, nullptr, 1, 0);
+  phase_fk(cx, C, W, k0);
+  role_barrier(cx, k0, nw);
+  phase_kin_residual(cx, C, W, x, W.c, k0, nw);
+  phase_kin_hessian(cx, C, W, k0, nw);
+  phase_kin_jacobian(cx, C, W, k0, nw);
   BMPC_SYNC();
   BMPC_TMARK(1);
-  phase_kin_residual(cx, C, W, x, W.c);
-  BMPC_TMARK(32);
-  phase_kin_hessian(cx, C, W);
-  BMPC_TMARK(33);
-  phase_kin_jacobian(cx, C, W);
-  BMPC_TMARK(34);
   phase_path_blocks(cx, C, W, p);
   BMPC_TMARK(35);
   phase_grad_f(cx, C, W, p, x, W.gradf);

@@ -545,49 +545,120 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
   return true;
 }
 
-// Forward sweep, executed by ONE warp (no CTA barriers inside): du_k = kappa_k + K_k ds_k,
-// dx_{k+1} = G_k (ds_k, du_k) + c_k.  The running (ds, du) vector lives in shared memory.
+// Operands of the single-warp sweeps (gains, kinematic rows, residuals) live in the global workspace: read where they
+// are used, every stage pays three to four L2 round trips on the critical path of the solve.  They are staged in the
+// shared memory of the idle Riccati blocks instead (S.ev[0 .. 3 FS_SIZE), below the sweep scratch S.YZ[0 .. 256)):
+// the warps that have no part in the sweep copy stage k + 2 with cp.async while warp 0 works on stage k.
+constexpr int FS_K = 0, FS_KAP = NU * NX, FS_GK = FS_KAP + NU, FS_C = FS_GK + NK * NZ, FS_SIZE = FS_C + NE;   // 1020 doubles
+static_assert(3 * FS_SIZE <= NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64, "sweep staging overlaps S.YZ");
+BMPC_DEV void fs_stage(const Ctx cx, const Work& W, double* buf, int k, int w0, int w1) {
+  const double* Kg = W.Kk + (size_t)k * NU * NX;
+  const double* rec = W.rec + (size_t)k * R_SIZE + R_GK;
+#pragma unroll 1
+  ROLE_FOR(i, FS_SIZE, w0, w1) {
+    const double* src = i < FS_KAP ? Kg + i : (i < FS_GK ? W.kap + k * NU + (i - FS_KAP) : (i < FS_C ? rec + (i - FS_GK) : W.c + NE * k + (i - FS_C)));
+    cp_async8(buf + i, src);
+  }
+}
+
+// Forward sweep: du_k = kappa_k + K_k ds_k, dx_{k+1} = G_k (ds_k, du_k) + c_k.  Called by the whole CTA: warp 0 runs the
+// recursion (warp-level barriers only; the running (ds, du) vector lives in shared memory), the other warps stage.
+// Lane roles per stage: (A) 8 rows of K x 4 column quarters; (B) lanes 0-7 finish du; (C) lanes 0-23 = 12 kinematic
+// rows x 2 column halves, lanes 24-31 = the three integrator rows of joint j = lane - 24 (7 = path parameter, same
+// code for all eight lanes); (D) lanes 0-11 finish the kinematic rows.
 BMPC_DEV void forward_sweep(const Ctx cx, const Config& C, const Work& W, Smem& S) {
   double* zb = S.YZ;            // [2][64]: z = (ds (44), du (8)) of the current / next stage
   double* part = S.YZ + 128;    // [32] partial sums
-  LANE_FOR(l, 128) zb[l] = 0.0;
-  BMPC_WSYNC();
-  for (int k = 0; k < C.N; k++) {
-    const double* GK = W.rec + (size_t)k * R_SIZE + R_GK;
-    const double* K = W.Kk + (size_t)k * NU * NX;
-    double* z = zb + 64 * (k & 1);
-    double* zn = zb + 64 * ((k + 1) & 1);
-    double* dw = W.dx + NX * k;
-    LANE_FOR(l, 32) {           // lane -> (row i of K, quarter of the columns)
-      const int i = l >> 2, c0 = 11 * (l & 3);
-      double a = 0.0;
-      if (k > 0) {
+  double* ring = S.ev;          // [3][FS_SIZE]
+  const int N = C.N, nw = ctx_nwarps(cx);
+#ifdef BMPC_HOST_EMU
+  const int p0 = 0;
+#else
+  const int p0 = 1;             // staging warps: [p0, nw)
+#endif
+  const bool lead = in_role(cx, 0, 1), prod = in_role(cx, p0, nw);
+  if (lead) LANE_FOR(l, 128) zb[l] = 0.0;
+  if (prod) {
+    fs_stage(cx, W, ring, 0, p0, nw);
+    cp_async_commit();
+    if (N > 1) fs_stage(cx, W, ring + FS_SIZE, 1, p0, nw);
+    cp_async_commit();
+    cp_async_wait_group1();
+  }
+  BMPC_SYNC();
+  for (int k = 0; k < N; k++) {
+    if (prod) {
+      if (k + 2 < N) fs_stage(cx, W, ring + FS_SIZE * ((k + 2) % 3), k + 2, p0, nw);   // (that buffer held stage k - 1)
+      cp_async_commit();
+    }
+    if (lead) {
+      const double* b = ring + FS_SIZE * (k % 3);
+      const double* K = b + FS_K;
+      const double* GK = b + FS_GK;
+      double* z = zb + 64 * (k & 1);
+      double* zn = zb + 64 * ((k + 1) & 1);
+      double* dw = W.dx + NX * k;
+      LANE_FOR(l, 32) {           // (A) lane -> (row i of K, quarter of the columns)
+        const int i = l >> 2, c0 = 11 * (l & 3);
+        double a = 0.0;
+        if (k > 0) {
+#ifdef BMPC_SPLIT_ACC
+          double a1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 11; j++) a += K[i * NX + c0 + j] * z[c0 + j];
+          for (int j = 0; j < 10; j += 2) { a += K[i * NX + c0 + j] * z[c0 + j]; a1 += K[i * NX + c0 + j + 1] * z[c0 + j + 1]; }
+          a = (a + K[i * NX + c0 + 10] * z[c0 + 10]) + a1;
+#else
+#pragma unroll
+          for (int j = 0; j < 11; j++) a += K[i * NX + c0 + j] * z[c0 + j];
+#endif
+        }
+        part[l] = a;
       }
-      part[l] = a;
-    }
-    BMPC_WSYNC();
-    LANE_FOR(i, NU) {
-      const double du = W.kap[k * NU + i] + ((part[4 * i] + part[4 * i + 1]) + (part[4 * i + 2] + part[4 * i + 3]));
-      z[NX + i] = du; zn[i] = du; dw[i] = du;
-    }
-    BMPC_WSYNC();
-    LANE_FOR(l, 24) {           // lane -> (kinematic row r, half of the columns)
-      const int r = l % 12, c0 = 26 * (l / 12);
-      double a = 0.0;
+      BMPC_WSYNC();
+      LANE_FOR(i, NU) {           // (B)
+        const double du = b[FS_KAP + i] + ((part[4 * i] + part[4 * i + 1]) + (part[4 * i + 2] + part[4 * i + 3]));
+        z[NX + i] = du; zn[i] = du; dw[i] = du;
+      }
+      BMPC_WSYNC();
+      LANE_FOR(l, 32) {           // (C)
+        if (l < 24) {
+          const int r = l % 12, c0 = 26 * (l / 12);
+#ifdef BMPC_SPLIT_ACC
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-      for (int j = 0; j < 26; j++) a += GK[r * NZ + c0 + j] * z[c0 + j];
-      part[l] = a;
+          for (int j = 0; j < 24; j += 4) {
+            a0 += GK[r * NZ + c0 + j] * z[c0 + j]; a1 += GK[r * NZ + c0 + j + 1] * z[c0 + j + 1];
+            a2 += GK[r * NZ + c0 + j + 2] * z[c0 + j + 2]; a3 += GK[r * NZ + c0 + j + 3] * z[c0 + j + 3];
+          }
+          a0 += GK[r * NZ + c0 + 24] * z[c0 + 24]; a1 += GK[r * NZ + c0 + 25] * z[c0 + 25];
+          part[l] = (a0 + a1) + (a2 + a3);
+#else
+          double a = 0.0;
+#pragma unroll
+          for (int j = 0; j < 26; j++) a += GK[r * NZ + c0 + j] * z[c0 + j];
+          part[l] = a;
+#endif
+        } else {
+          const int j = l - 24;
+          const double um = z[tcol(j, 0)], q = z[tcol(j, 1)], dq = z[tcol(j, 2)], ddq = z[tcol(j, 3)], u = z[NX + j];
+          const int r0 = trow(j, 0), r1 = trow(j, 1), r2 = trow(j, 2);
+          // (same order of operations as G_vec)
+          double g0 = C.a_u * u; g0 += q + C.a_dq * dq + C.a_ddq * ddq + C.a_um * um;
+          double g1 = C.b_u * u; g1 += dq + C.b_ddq * ddq + C.b_um * um;
+          double g2 = C.c_u * u; g2 += ddq + C.c_um * um;
+          const double v0 = b[FS_C + r0] + g0, v1 = b[FS_C + r1] + g1, v2 = b[FS_C + r2] + g2;
+          zn[8 + r0] = v0; dw[8 + r0] = v0; zn[8 + r1] = v1; dw[8 + r1] = v1; zn[8 + r2] = v2; dw[8 + r2] = v2;
+        }
+      }
+      BMPC_WSYNC();
+      LANE_FOR(l, NK) {           // (D)
+        const double v = b[FS_C + rKIN + l] + (part[l] + part[l + 12]);
+        zn[8 + rKIN + l] = v; dw[8 + rKIN + l] = v;
+      }
+      BMPC_WSYNC();
     }
-    BMPC_WSYNC();
-    LANE_FOR(i, NE) {
-      double v = W.c[NE * k + i];
-      if (i >= rKIN && i < rKIN + NK) v += part[i - rKIN] + part[i - rKIN + 12];
-      else v += G_vec(C, nullptr, z, z + NX, i);
-      zn[8 + i] = v; dw[8 + i] = v;
-    }
-    BMPC_WSYNC();
+    if (prod) cp_async_wait_group1();   // stage k + 1 has landed
+    BMPC_SYNC();
   }
 }
 
@@ -597,8 +668,16 @@ BMPC_DEV void forward_sweep(const Ctx cx, const Config& C, const Work& W, Smem& 
 // uses d q_n = dw_{k+1}[q] - c_{k+1}[q rows] (the linearised change of the integrated state).
 BMPC_DEV void adjoint_rhs(const Ctx cx, const Config& C, const Work& W, const KktCoef& kc, const Smem& S, double delta_w) {
   const double ovv = -2 * kc.w5 * kc.idt * kc.idt;
-  PAR_FOR(it, C.N * NE) {
-    const int k = it / NE, r = 8 + it - NE * k;
+  // Items in row-class order (joint rows q / dq / ddq, the y rows, the v rows, ddphi), stage-minor: the classes take
+  // different branches below, each with its own reads from the global stage records, and a warp whose lanes sit in
+  // one class pays one such round trip instead of one per class.
+  const int N = C.N;
+  PAR_FOR(it, N * NE) {
+    int k, r;
+    if (it < 21 * N) { const int t = it / (7 * N), q = it - 7 * N * t; k = q / 7; r = 8 + 7 * t + (q - 7 * k); }
+    else if (it < 29 * N) { const int q = it - 21 * N; k = q >> 3; r = yrow(q & 7); }
+    else if (it < 35 * N) { const int q = it - 29 * N; k = q / 6; r = oVLIN + (q - 6 * k); }
+    else { k = it - 35 * N; r = oDDPHI; }
     const bool has_next = k + 1 < C.N;
     const double* rec = W.rec + (size_t)k * R_SIZE;
     const double* rn = rec + R_SIZE;
@@ -637,22 +716,47 @@ BMPC_DEV void adjoint_rhs(const Ctx cx, const Config& C, const Work& W, const Kk
       }
       a += S.alc[t] * hq + S.bec[t] * hd + hk;
     }
-    W.ynew[it] = a;
+    W.ynew[NE * k + r - 8] = a;
   }
 }
 
-// Adjoint recursion y_k = r_k + [A_hat_{k+1}^T y_{k+1}]_x, executed by ONE warp.
+// Adjoint recursion y_k = r_k + [A_hat_{k+1}^T y_{k+1}]_x, executed by ONE warp.  Of the columns 8..43 of the kinematic
+// rows GK only 8..28 (q, dq, ddq of the previous block) are ever non-zero, plus the identity of the p_rot columns
+// (phase_kin_jacobian_init / phase_kin_jacobian): those 12 x 21 entries of the stages N-1, N-2, ... are staged in shared
+// memory by the whole CTA (adjoint_stage, issued before the right-hand side is built, complete after it) as far as the
+// idle Riccati blocks have room (12 stages); earlier stages of longer horizons are read from the workspace.
+constexpr int AS_COLS = 21, AS_SIZE = NK * AS_COLS, AS_MAX = 12;
+static_assert(AS_MAX * AS_SIZE <= 3 * FS_SIZE, "adjoint staging overlaps S.YZ");
+BMPC_DEV int adjoint_slots(int N) { return N - 1 < AS_MAX ? N - 1 : AS_MAX; }
+BMPC_DEV void adjoint_stage(const Ctx cx, const Config& C, const Work& W, Smem& S) {
+  const int ns = adjoint_slots(C.N);
+#pragma unroll 1
+  PAR_FOR(it, ns * AS_SIZE) {
+    const int slot = it / AS_SIZE, q = it - AS_SIZE * slot, r = q / AS_COLS, cc = q - AS_COLS * r;
+    cp_async8(S.ev + it, W.rec + (size_t)(C.N - 1 - slot) * R_SIZE + R_GK + r * NZ + 8 + cc);
+  }
+}
 BMPC_DEV void adjoint_sweep(const Ctx cx, const Config& C, const Work& W, Smem& S) {
   double* yb = S.YZ;            // [2][40]
-  const int N = C.N;
+  const int N = C.N, ns = adjoint_slots(N);
   LANE_FOR(i, NE) yb[40 * ((N - 1) & 1) + i] = W.ynew[NE * (N - 1) + i];
   BMPC_WSYNC();
   for (int k = N - 2; k >= 0; k--) {
-    const double* GKn = W.rec + (size_t)(k + 1) * R_SIZE + R_GK;
+    const int slot = N - 2 - k;   // of stage k + 1
+    const double* g = slot < ns ? S.ev + slot * AS_SIZE : W.rec + (size_t)(k + 1) * R_SIZE + R_GK + 8;
+    const int gs = slot < ns ? AS_COLS : NZ;
     const double* yn = yb + 40 * ((k + 1) & 1);
     double* yc = yb + 40 * (k & 1);
     LANE_FOR(i, NE) {
-      const double v = W.ynew[NE * k + i] + GT_tab(S, GKn, yn, 8 + i);
+      // (G^T y)[8 + i] with the terms in the order of GT_tab; the structural zeros contribute nothing
+      double a = 0.0;
+      if (i < AS_COLS) {
+#pragma unroll
+        for (int r = 0; r < NK; r++) a += g[r * gs + i] * yn[rKIN + r];
+      } else if (i >= oPROT - 8 && i < oPROT - 8 + 3) a += yn[i];
+#pragma unroll
+      for (int t = 0; t < 3; t++) a += S.tcc[3 * (8 + i) + t] * yn[S.tcr[3 * (8 + i) + t]];
+      const double v = W.ynew[NE * k + i] + a;
       W.ynew[NE * k + i] = v;
       yc[i] = v;
     }
@@ -673,10 +777,11 @@ BMPC_NOINLINE bool kkt_solve(const Ctx cx, const Config& C, const Work& W, const
   BMPC_TMARK(7);
   for (int k = C.N - 1; k >= 0; k--)
     if (!riccati_stage(cx, C, W, kc, S, k, delta_w)) return false;
-  if (ctx_warp(cx) == 0) forward_sweep(cx, C, W, S);
-  BMPC_SYNC();
+  forward_sweep(cx, C, W, S);
   BMPC_TMARK(14);
+  adjoint_stage(cx, C, W, S);
   adjoint_rhs(cx, C, W, kc, S, delta_w);
+  cp_async_wait();
   BMPC_SYNC();
   BMPC_TMARK(15);
   if (ctx_warp(cx) == 0) adjoint_sweep(cx, C, W, S);
