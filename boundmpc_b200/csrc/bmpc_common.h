@@ -301,6 +301,14 @@ BMPC_DEV void cp_async8(double* dst_smem, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 #endif
 }
+BMPC_DEV void cp_async16(double* dst_smem, const double* src) {   // two doubles, both addresses 16-byte aligned
+#ifdef BMPC_HOST_EMU
+  dst_smem[0] = src[0]; dst_smem[1] = src[1];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+#endif
+}
 BMPC_DEV void cp_async_wait() {
 #ifndef BMPC_HOST_EMU
   asm volatile("cp.async.wait_all;" ::: "memory");

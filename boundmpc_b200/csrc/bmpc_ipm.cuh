@@ -245,12 +245,12 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       double jd = JD[6] * dw[oPHI] + JD[7] * dw[oDPHI];
       for (int q = 0; q < 6; q++) jd += JD[q] * dw[oPPOS + q];
       const double sv = W.s[i], zv = W.zs[i];
-      const double dsv = -(W.d[i] + sv) - jd;
-      const double dzv = mu / sv - zv - zv / sv * dsv;
+      const double dsv = -(W.d[i] + sv) - jd, isv = 1.0 / sv;
+      const double dzv = mu * isv - zv - zv * isv * dsv;
       W.ds[i] = dsv; W.dzs[i] = dzv;
       if (dsv < 0) sv4[0] = fmin(sv4[0], -tau * sv / dsv);
       if (dzv < 0) sv4[1] = fmin(sv4[1], -tau * zv / dzv);
-      sv4[2] -= mu * dsv / sv;
+      sv4[2] -= mu * dsv * isv;
       sv4[3] -= mu * bmpc_log(sv);
     }
     PAR_FOR(i, n) {
@@ -259,19 +259,19 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       double dl = 0.0, du = 0.0;
       sv4[2] += W.gradf[i] * dxi;
       if (l > -1e300) {
-        const double sl = W.x[i] - l, z = W.zL[i];
-        dl = mu / sl - z - z / sl * dxi;
+        const double sl = W.x[i] - l, z = W.zL[i], isl = 1.0 / sl;
+        dl = mu * isl - z - z * isl * dxi;
         if (dxi < 0) sv4[0] = fmin(sv4[0], -tau * sl / dxi);
         if (dl < 0) sv4[1] = fmin(sv4[1], -tau * z / dl);
-        sv4[2] -= mu * dxi / sl;
+        sv4[2] -= mu * dxi * isl;
         sv4[3] -= mu * bmpc_log(sl);
       }
       if (u < 1e300) {
-        const double su = u - W.x[i], z = W.zU[i];
-        du = mu / su - z + z / su * dxi;
+        const double su = u - W.x[i], z = W.zU[i], isu = 1.0 / su;
+        du = mu * isu - z + z * isu * dxi;
         if (dxi > 0) sv4[0] = fmin(sv4[0], tau * su / dxi);
         if (du < 0) sv4[1] = fmin(sv4[1], -tau * z / du);
-        sv4[2] += mu * dxi / su;
+        sv4[2] += mu * dxi * isu;
         sv4[3] -= mu * bmpc_log(su);
       }
       W.dzL[i] = dl; W.dzU[i] = du;
@@ -348,20 +348,21 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       }
     }
     // ---- accept the step; keep the multipliers within Ipopt's kappa_Sigma band
-    const double ks = 1e10;
+    const double ks = 1e10, iks = 1e-10;
     PAR_FOR(i, n) {
       const int a = i % NX;
       const double l = C.lb[a], u = C.ub[a];
       const double xn = W.x[i] + alpha * W.dx[i];
       W.x[i] = xn;
-      if (l > -1e300) { const double sl = xn - l; double z = W.zL[i] + adu * W.dzL[i]; W.zL[i] = fmax(fmin(z, ks * mu / sl), mu / (ks * sl)); }
-      if (u < 1e300) { const double su = u - xn; double z = W.zU[i] + adu * W.dzU[i]; W.zU[i] = fmax(fmin(z, ks * mu / su), mu / (ks * su)); }
+      if (l > -1e300) { const double ms = mu / (xn - l); double z = W.zL[i] + adu * W.dzL[i]; W.zL[i] = fmax(fmin(z, ks * ms), ms * iks); }
+      if (u < 1e300) { const double ms = mu / (u - xn); double z = W.zU[i] + adu * W.dzU[i]; W.zU[i] = fmax(fmin(z, ks * ms), ms * iks); }
     }
     PAR_FOR(i, nd) {
       const double sn = W.s[i] + alpha * W.ds[i];
       W.s[i] = sn;
       const double z = W.zs[i] + adu * W.dzs[i];
-      W.zs[i] = fmax(fmin(z, ks * mu / sn), mu / (ks * sn));
+      const double ms = mu / sn;
+      W.zs[i] = fmax(fmin(z, ks * ms), ms * iks);
     }
     PAR_FOR(i, ne) W.y[i] += alpha * (W.ynew[i] - W.y[i]);
     BMPC_SYNC();

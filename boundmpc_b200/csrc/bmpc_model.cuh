@@ -584,13 +584,13 @@ BMPC_NOINLINE void eval_values(const Ctx cx, const Config& C, const Work& W, con
   phase_integrate(cx, C, W, x, c);
   BMPC_SYNC();
   BMPC_TMARK(3);
+  // warp 0: the kinematic chains, then (warp-level barrier) the 3 N residual items that need them; warp 1: path terms
   phase_fk(cx, C, W);
+  if (in_role(cx, 0, 1)) { BMPC_WSYNC(); }
+  phase_kin_residual(cx, C, W, x, c, 0, 1);
   phase_path(cx, C, W, p, x, d, nullptr, 0, 1);
   BMPC_SYNC();
   BMPC_TMARK(4);
-  phase_kin_residual(cx, C, W, x, c, 0, ctx_nwarps(cx));
-  BMPC_SYNC();
-  BMPC_TMARK(5);
 }
 
 // The path terms with derivatives are by far the longest serial piece of an evaluation (one lane per stage, several

@@ -214,8 +214,9 @@ BMPC_DEV void kkt_prepare(const Ctx cx, const Config& C, const Work& W, double m
     const int k = gi / NX, a = gi - NX * k;
     double gb = W.gradf[gi], sg = 0.0;
     const double lb = C.lb[a], ub = C.ub[a];
-    if (lb > -1e300) { const double sl = W.x[gi] - lb; gb -= mu / sl; sg += W.zL[gi] / sl; }
-    if (ub < 1e300) { const double su = ub - W.x[gi]; gb += mu / su; sg += W.zU[gi] / su; }
+    // (one reciprocal per bound: the IEEE divide is ~30 instructions of dependent latency, and these loops are made of them)
+    if (lb > -1e300) { const double isl = 1.0 / (W.x[gi] - lb); gb -= mu * isl; sg += W.zL[gi] * isl; }
+    if (ub < 1e300) { const double isu = 1.0 / (ub - W.x[gi]); gb += mu * isu; sg += W.zU[gi] * isu; }
     const int ya = yidx(a);
     if (ya >= 0) { const double* rec = W.rec + (size_t)k * R_SIZE; gb += mu * rec[R_GJ1 + ya] + rec[R_GJ2 + ya]; }
     W.gh[gi] = gb;
@@ -335,7 +336,12 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 #pragma unroll
     for (int l = 0; l < j; l++) d -= A[j][l] * A[j][l];
     if (!(d > 1e-14)) ok = false;
+    // (device: rsqrt, 1 ulp; eight inlined IEEE sqrt + divide pairs were 6.5 KB of the stage's instruction stream)
+#if defined(BMPC_HOST_EMU) || defined(BMPC_IEEE_CHOL)
     const double inv = 1.0 / sqrt(d > 1e-14 ? d : 1.0);
+#else
+    const double inv = rsqrt(d > 1e-14 ? d : 1.0);
+#endif
     A[j][j] = inv;
 #pragma unroll
     for (int i = j + 1; i < NU; i++) {
@@ -550,14 +556,18 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
 // shared memory of the idle Riccati blocks instead (S.ev[0 .. 3 FS_SIZE), below the sweep scratch S.YZ[0 .. 256)):
 // the warps that have no part in the sweep copy stage k + 2 with cp.async while warp 0 works on stage k.
 constexpr int FS_K = 0, FS_KAP = NU * NX, FS_GK = FS_KAP + NU, FS_C = FS_GK + NK * NZ, FS_SIZE = FS_C + NE;   // 1020 doubles
+static_assert(FS_KAP % 2 == 0 && FS_GK % 2 == 0 && FS_C % 2 == 0 && FS_SIZE % 2 == 0 && R_SIZE % 2 == 0 && NE % 2 == 0, "16-byte staging");
 static_assert(3 * FS_SIZE <= NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64, "sweep staging overlaps S.YZ");
 BMPC_DEV void fs_stage(const Ctx cx, const Work& W, double* buf, int k, int w0, int w1) {
+  // 16-byte copies: every segment starts at an even offset of the 256-byte aligned workspace slice / of S.ev
   const double* Kg = W.Kk + (size_t)k * NU * NX;
-  const double* rec = W.rec + (size_t)k * R_SIZE + R_GK;
-#pragma unroll 1
-  ROLE_FOR(i, FS_SIZE, w0, w1) {
-    const double* src = i < FS_KAP ? Kg + i : (i < FS_GK ? W.kap + k * NU + (i - FS_KAP) : (i < FS_C ? rec + (i - FS_GK) : W.c + NE * k + (i - FS_C)));
-    cp_async8(buf + i, src);
+  const double* kg = W.kap + k * NU;
+  const double* rg = W.rec + (size_t)k * R_SIZE + R_GK;
+  const double* cg = W.c + NE * k;
+#pragma unroll 2
+  ROLE_FOR(h, FS_SIZE / 2, w0, w1) {
+    const int i = 2 * h;
+    cp_async16(buf + i, i < FS_KAP ? Kg + i : (i < FS_GK ? kg + (i - FS_KAP) : (i < FS_C ? rg + (i - FS_GK) : cg + (i - FS_C))));
   }
 }
 
