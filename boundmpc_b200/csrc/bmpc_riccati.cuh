@@ -457,8 +457,14 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
       S.M[a * LDM + b] = v;
     }
   }
-  PAR_FOR(it, 12 * NX) {           // rows p_pos, p_rot, v: no integrator part
-    const int a = oPPOS + it / NX, b = it - NX * (it / NX);
+  // rows p_pos, p_rot, v: no integrator part.  Phase 5 reads Q_ss only through the upper tiles (tile row <= tile
+  // column) and writes P_k symmetrically, so of these 12 rows only the columns from the first column of their tile
+  // row on are needed: 3 x 20 + 8 x 12 + 4 = 160 entries instead of 528.
+  PAR_FOR(it, 160) {
+    int a, b;
+    if (it < 60) { a = 29 + it / 20; b = 24 + it - 20 * (it / 20); }
+    else if (it < 156) { const int q = it - 60; a = 32 + q / 12; b = 32 + q - 12 * (q / 12); }
+    else { a = 40; b = 40 + it - 156; }
     double v = 0.0;
     if (b >= oVLIN && b < oVLIN + 6) v += GKs[(6 + b - oVLIN) * NZ + a] * ovv;
     if (a >= oVLIN && a < oVLIN + 6) {
@@ -558,7 +564,7 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
 constexpr int FS_K = 0, FS_KAP = NU * NX, FS_GK = FS_KAP + NU, FS_C = FS_GK + NK * NZ, FS_SIZE = FS_C + NE;   // 1020 doubles
 static_assert(FS_KAP % 2 == 0 && FS_GK % 2 == 0 && FS_C % 2 == 0 && FS_SIZE % 2 == 0 && R_SIZE % 2 == 0 && NE % 2 == 0, "16-byte staging");
 static_assert(3 * FS_SIZE <= NX * LDM + (NK * NZ + 4) + 2 * (4 * 49 + 4) + (64 + 8 + NX) + NX + 64, "sweep staging overlaps S.YZ");
-BMPC_DEV void fs_stage(const Ctx cx, const Work& W, double* buf, int k, int w0, int w1) {
+BMPC_NOINLINE void fs_stage(const Ctx cx, const Work& W, double* buf, int k, int w0, int w1) {   // (one copy: three call sites)
   // 16-byte copies: every segment starts at an even offset of the 256-byte aligned workspace slice / of S.ev
   const double* Kg = W.Kk + (size_t)k * NU * NX;
   const double* kg = W.kap + k * NU;
