@@ -321,10 +321,14 @@ BMPC_DEV TrivOut triv_combine(const Config& C, double m1, double m2, double m3) 
 BMPC_DEV int trow(int j, int t) { return j < 7 ? 7 * t + j : 33 + t; }              // t = 0, 1, 2
 BMPC_DEV int tcol(int j, int t) { return j < 7 ? (t == 0 ? oU : (t == 1 ? oQ : (t == 2 ? oDQ : oDDQ))) + j : (t == 0 ? oUPHI : oPHI + t - 1); }   // t = 0..3
 
-// 8 x 8 Cholesky factor of Q_uu in registers; Lr holds L with the RECIPROCAL diagonal.  Every thread
-// that needs the factor computes it itself from shared memory (no broadcast, no extra barrier; the
-// result is identical in all threads, so the inertia verdict is CTA-uniform).
-BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
+// b := Q_uu^{-1} b by an 8 x 8 Cholesky factorisation in registers (L kept with the RECIPROCAL diagonal) and two
+// triangular solves.  Every thread that has a column to solve factorises Q_uu itself from shared memory (no
+// broadcast, no extra barrier; the verdict is the same in all of them, so the inertia test is CTA-uniform).
+// Factorisation and forward substitution run in ONE unrolled pass: row j of the substitution only needs pivot j and
+// the columns < j of L, so its dependency chain runs in the shadow of the factorisation's instead of after it.
+// (device: rsqrt, 1 ulp; eight inlined IEEE sqrt + divide pairs were 6.5 KB of the stage's instruction stream)
+BMPC_DEV bool chol8_solve(const double* Qu, double (&b)[NU]) {
+  double A[NU][NU];
 #pragma unroll
   for (int i = 0; i < NU; i++)
 #pragma unroll
@@ -336,7 +340,6 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
 #pragma unroll
     for (int l = 0; l < j; l++) d -= A[j][l] * A[j][l];
     if (!(d > 1e-14)) ok = false;
-    // (device: rsqrt, 1 ulp; eight inlined IEEE sqrt + divide pairs were 6.5 KB of the stage's instruction stream)
 #if defined(BMPC_HOST_EMU) || defined(BMPC_IEEE_CHOL)
     const double inv = 1.0 / sqrt(d > 1e-14 ? d : 1.0);
 #else
@@ -350,6 +353,17 @@ BMPC_DEV bool chol8(const double* Qu, double (&A)[NU][NU]) {
       for (int l = 0; l < j; l++) e -= A[i][l] * A[j][l];
       A[i][j] = e * inv;
     }
+    double a = b[j];
+#pragma unroll
+    for (int l = 0; l < j; l++) a -= A[j][l] * b[l];
+    b[j] = a * inv;
+  }
+#pragma unroll
+  for (int i = NU - 1; i >= 0; i--) {
+    double a = b[i];
+#pragma unroll
+    for (int l = i + 1; l < NU; l++) a -= A[l][i] * b[l];
+    b[i] = a * A[i][i];
   }
   return ok;
 }
@@ -480,37 +494,17 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
   // thread, each with its own register copy of the 8 x 8 factor).  Other warps: stage the data of stage k - 1.
   double* K = W.Kk + (size_t)k * NU * NX;
   double* kap = W.kap + k * NU;
-  if (in_role(cx, 0, 2)) {
-    double L[NU][NU];
-    const bool okc = chol8(S.Qu, L);
-    BMPC_TMARK(41);
-    if (!okc) S.flag[3] = 1;
-    else {
-      ROLE_FOR(col, (first ? 0 : NX) + 1, 0, 2) {
-        const bool isk = col == (first ? 0 : NX);
-        double bcol[NU];
+  // (factorisation and forward substitution fused, see chol8_solve; a thread without a column has nothing to do)
+  ROLE_FOR(col, (first ? 0 : NX) + 1, 0, 2) {
+    const bool isk = col == (first ? 0 : NX);
+    double bcol[NU];
 #pragma unroll
-        for (int i = 0; i < NU; i++) bcol[i] = isk ? -S.qv[NX + i] : -S.Qu[col * LDQ + i];
+    for (int i = 0; i < NU; i++) bcol[i] = isk ? -S.qv[NX + i] : -S.Qu[col * LDQ + i];
+    if (!chol8_solve(S.Qu, bcol)) S.flag[3] = 1;
 #pragma unroll
-        for (int i = 0; i < NU; i++) {
-          double a = bcol[i];
-#pragma unroll
-          for (int l = 0; l < i; l++) a -= L[i][l] * bcol[l];
-          bcol[i] = a * L[i][i];
-        }
-#pragma unroll
-        for (int i = NU - 1; i >= 0; i--) {
-          double a = bcol[i];
-#pragma unroll
-          for (int l = i + 1; l < NU; l++) a -= L[l][i] * bcol[l];
-          bcol[i] = a * L[i][i];
-        }
-#pragma unroll
-        for (int i = 0; i < NU; i++) {
-          if (isk) { kap[i] = bcol[i]; S.kapv[i] = bcol[i]; }
-          else { K[i * NX + col] = bcol[i]; S.Ks[i * NX + col] = bcol[i]; }
-        }
-      }
+    for (int i = 0; i < NU; i++) {
+      if (isk) { kap[i] = bcol[i]; S.kapv[i] = bcol[i]; }
+      else { K[i * NX + col] = bcol[i]; S.Ks[i * NX + col] = bcol[i]; }
     }
   }
   BMPC_TMARK(42);
