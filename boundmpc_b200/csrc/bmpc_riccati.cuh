@@ -524,16 +524,20 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
   // ---- phase 5: P_k = Q_ss + Q_su K (symmetric: upper tiles, mirrored), p_k = q_s + Q_su kappa
   for (int ti = ctx_warp(cx); ti < 6; ti = nw == 4 ? ((ti == 2 || ti == 3) ? 7 - ti : 6) : ti + nw) {   // 4 warps: 6, 5, 4 + 1, 3 + 2 tiles
     const int nt = 6 - ti;
-    mma_rowblock<5, 6>(cx, nt,
-        [&](int r, int kk) { return kk < NK ? GKs[kk * NZ + 8 * ti + r] : S.Qu[(8 * ti + r) * LDQ + kk - NK]; },
-        [&](int tt, int kk, int c) { return kk < NK ? S.YZ[(8 + rKIN + kk) * LDY + 8 * (ti + tt) + c] : S.Ks[(kk - NK) * NX + 8 * (ti + tt) + c]; },
-        [&](int tt, int r, int c) { const int a = 8 * ti + r, b = 8 * (ti + tt) + c; return (a < NX && b < NX) ? S.M[a * LDM + b] : 0.0; },
-        [&](int tt, int r, int c, double v) {
-          const int a = 8 * ti + r, b = 8 * (ti + tt) + c;
-          if (a >= NX || b >= NX || a > b) return;
-          S.M[a * LDM + b] = v;
-          S.M[b * LDM + a] = v;
-        });
+    auto fa = [&](int r, int kk) { return kk < NK ? GKs[kk * NZ + 8 * ti + r] : S.Qu[(8 * ti + r) * LDQ + kk - NK]; };
+    auto fb = [&](int tt, int kk, int c) { return kk < NK ? S.YZ[(8 + rKIN + kk) * LDY + 8 * (ti + tt) + c] : S.Ks[(kk - NK) * NX + 8 * (ti + tt) + c]; };
+    auto fc = [&](int tt, int r, int c) { const int a = 8 * ti + r, b = 8 * (ti + tt) + c; return (a < NX && b < NX) ? S.M[a * LDM + b] : 0.0; };
+    auto fe = [&](int tt, int r, int c, double v) {
+      const int a = 8 * ti + r, b = 8 * (ti + tt) + c;
+      if (a >= NX || b >= NX || a > b) return;
+      S.M[a * LDM + b] = v;
+      S.M[b * LDM + a] = v;
+    };
+    // (a pass walks through the code of all NT tile slots whatever nt is: the short row blocks, which are the second
+    // pass of their warps, get narrower instantiations)
+    if (nt > 4) mma_rowblock<5, 6>(cx, nt, fa, fb, fc, fe);
+    else if (nt > 2) mma_rowblock<5, 4>(cx, nt, fa, fb, fc, fe);
+    else mma_rowblock<5, 2>(cx, nt, fa, fb, fc, fe);
   }
   BMPC_TMARK(30);
   BMPC_TMARK2(45);
