@@ -422,7 +422,7 @@ def main():
     line = {"metric": METRIC, "value": total * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": max(1, world),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "roofline": {"bound": "fp64", "achieved": ach / 1e12, "peak": peak_dfma / 1e12, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 on the tensor sub-pipe, same issue rate as DFMA)", "achieved": ach / 1e12, "peak": peak_dfma / 1e12, "unit": "TFLOP/s",
                          "frac": ach / peak_dfma, "traffic": traffic,
                          "note": "k_solve, algorithmic flops = sum of interior-point iterations x 2.97 MFLOP (SURVEY 8d) / mean "
                                  "CUDA-event launch duration; peak = DFMA loop measured in this run (no FP64 entry in "
