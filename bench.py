@@ -200,8 +200,14 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist
+    json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # (NCCL's version banner off stdout: one JSON line only)
+        # one JSON line on stdout and nothing else: NCCL prints its version banner on file descriptor 1 whatever
+        # NCCL_DEBUG_FILE says, so fd 1 is pointed at stderr for the run and the line goes to a saved copy of it
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peak_dfma = solver.fp64_peak(0)
@@ -451,7 +457,12 @@ def main():
                                 "sample": f"first {d} instances of the workload in {el:.1f} s, oracle/ interior-point port at tol "
                                           f"{TOL:g} on {cores} threads (CasADi/Ipopt not installable offline), mean {itm:.1f} "
                                           f"iterations, {fl} failures"}
-    print(json.dumps(line))
+    if json_fd is None:
+        print(json.dumps(line))
+    else:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
     return 0
