@@ -31,7 +31,7 @@ from boundmpc_b200.ocp import default_solver
 from boundmpc_b200 import batches
 B, outp = int(sys.argv[2]), sys.argv[3]
 s = default_solver()
-x0, p = batches.make_batch(s, ("exp1", "exp2"), 0, B, bound_scale=True)
+x0, p = batches.make_batch(s, ("exp1", "exp2"), int(os.environ.get("AB_FIRST", "0")), B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 out = s.solve_batch(xd, pd); torch.cuda.synchronize()
 best = 1e9
