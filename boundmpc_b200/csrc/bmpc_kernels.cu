@@ -110,6 +110,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
     work_attach_smem(S.work, S, C0.N);
   }
   __syncthreads();
+#ifdef BMPC_PROBE_SLOTS   // development aid (scripts/probe_slots.py): SM and hardware warp slots of a few CTAs
+  if ((threadIdx.x & 31) == 0 && (blockIdx.x < 3 || (blockIdx.x >= 148 && blockIdx.x < 151) || (blockIdx.x >= 296 && blockIdx.x < 299))) {
+    unsigned wslot, smid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("cta %d warp %d smid %u warpid %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), smid, wslot);
+  }
+#endif
   const Config& C = S.cfg;
   const Work& W = S.work;
   build_tables(cx, C, S);
