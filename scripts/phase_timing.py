@@ -6,13 +6,12 @@ import numpy as np, torch
 from boundmpc_b200.ocp import default_solver
 from boundmpc_b200 import batches, _cabi
 
-NAMES = {0: "full: integrate+sincos", 1: "full: fk | path<1> | GK zero", 2: "full: residual, kin hess/jac, path blocks, grad f",
-         3: "values: integrate+sincos", 4: "values: fk | path<0>", 5: "values: kin residual", 6: "kkt error + reduce",
+NAMES = {0: "full: integrate+sincos", 1: "full: path<1> | fk -> kin residual, curvature, jacobian rows", 2: "full: end barrier",
+         3: "values: integrate+sincos", 4: "values: fk + kin residual | path<0>", 6: "kkt error + reduce",
          7: "kkt_solve init + prefetch", 8: "riccati 1: add_W", 9: "riccati 2a: Y integrator pass, tv", 10: "riccati 2b: Y dmma",
          11: "riccati 3: Qu, qv", 12: "riccati 4: chol+gains | Qss pass + prefetch", 13: "riccati 5: P dmma, pv",
-         14: "forward sweep", 15: "adjoint rhs", 16: "adjoint sweep", 17: "kkt_prepare", 18: "step parts + ftb reduce",
-         19: "ls: trial point", 20: "ls: merit reduce", 21: "accept step", 22: "init point", 23: "report", 30: "  riccati 5: dmma tiles (warp 0)", 31: "  riccati 5: pv", 32: "  full: kin residual (warp 0)",
-         33: "  full: kin hessian", 34: "  full: kin jacobian", 35: "  full: path blocks", 36: "  full: grad f", 40: "  riccati 5: flag check", 41: "  riccati 4: chol8 (thread 0)", 42: "  riccati 4: triangular solves (thread 0)", 48: "  [thread 64] up to phase 4", 49: "  [thread 64] riccati 4: prefetch issue", 50: "  [thread 64] riccati 4: Qss pass 1", 51: "  [thread 64] riccati 4: Qss pass 2", 52: "  [thread 64] riccati 4: cp.async wait", 44: "  [thread 64] everything up to phase 5", 45: "  [thread 64] riccati 5 tiles",
+         14: "forward sweep (warp 0) | staging (other warps)", 15: "adjoint staging + rhs", 16: "adjoint sweep", 17: "kkt_prepare", 18: "step parts + ftb reduce",
+         19: "ls: trial point", 20: "ls: merit reduce", 21: "accept step", 22: "init point", 23: "report", 30: "  riccati 5: dmma tiles (warp 0)", 31: "  riccati 5: pv", 35: "  full: path blocks", 36: "  full: grad f", 40: "  riccati 5: flag check", 42: "  riccati 4: factorisation + solves (thread 0)", 48: "  [thread 64] up to phase 4", 49: "  [thread 64] riccati 4: prefetch issue", 50: "  [thread 64] riccati 4: Qss pass 1", 51: "  [thread 64] riccati 4: Qss pass 2", 52: "  [thread 64] riccati 4: cp.async wait", 44: "  [thread 64] everything up to phase 5", 45: "  [thread 64] riccati 5 tiles",
          46: "  [thread 64] riccati 5 pv", 47: "  [thread 64] riccati 5 end barrier"}
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 s = default_solver()
