@@ -563,17 +563,32 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   cudaStream_t st = h->stream;
   CU(cudaMemcpyAsync(d + o_x0, x0, B * n * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
-  rc = bmpc_solve_batch(h, batch, (double*)(d + o_x0), (double*)(d + o_p), (double*)(d + o_x), (double*)(d + o_g), (double*)(d + o_lg),
-                        (double*)(d + o_lx), (double*)(d + o_f), (int32_t*)(d + o_it), (int32_t*)(d + o_st), (double*)(d + o_k), d + o_ws, st);
+  // Results.  A result buffer in page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister,
+  // e.g. a pinned torch tensor) is written by the kernel itself: every instance stores its 14 KB of results when its
+  // solve ends, so the transfer runs under the launch instead of after it (114 MB per 8,192 instances otherwise).
+  // Anything else gets a device buffer and a copy.  (Inputs are always copied: p is read throughout the solve.)
+  auto mapped = [&](const void* host) -> void* {
+    if (!host || getenv("BMPC_NO_ZERO_COPY")) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+  };
+  void *m_x = mapped(x), *m_g = mapped(g), *m_lg = mapped(lam_g), *m_lx = mapped(lam_x), *m_f = mapped(f), *m_k = mapped(kkt_err),
+       *m_it = mapped(iters), *m_st = mapped(status);
+  rc = bmpc_solve_batch(h, batch, (double*)(d + o_x0), (double*)(d + o_p), m_x ? (double*)m_x : (double*)(d + o_x),
+                        m_g ? (double*)m_g : (double*)(d + o_g), m_lg ? (double*)m_lg : (double*)(d + o_lg),
+                        m_lx ? (double*)m_lx : (double*)(d + o_lx), m_f ? (double*)m_f : (double*)(d + o_f),
+                        m_it ? (int32_t*)m_it : (int32_t*)(d + o_it), m_st ? (int32_t*)m_st : (int32_t*)(d + o_st),
+                        m_k ? (double*)m_k : (double*)(d + o_k), d + o_ws, st);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(x, d + o_x, B * n * 8, cudaMemcpyDeviceToHost, st));
-  if (g) CU(cudaMemcpyAsync(g, d + o_g, B * m * 8, cudaMemcpyDeviceToHost, st));
-  if (lam_g) CU(cudaMemcpyAsync(lam_g, d + o_lg, B * m * 8, cudaMemcpyDeviceToHost, st));
-  if (lam_x) CU(cudaMemcpyAsync(lam_x, d + o_lx, B * n * 8, cudaMemcpyDeviceToHost, st));
-  if (f) CU(cudaMemcpyAsync(f, d + o_f, B * 8, cudaMemcpyDeviceToHost, st));
-  if (kkt_err) CU(cudaMemcpyAsync(kkt_err, d + o_k, B * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(iters, d + o_it, B * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(status, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
+  if (!m_x) CU(cudaMemcpyAsync(x, d + o_x, B * n * 8, cudaMemcpyDeviceToHost, st));
+  if (g && !m_g) CU(cudaMemcpyAsync(g, d + o_g, B * m * 8, cudaMemcpyDeviceToHost, st));
+  if (lam_g && !m_lg) CU(cudaMemcpyAsync(lam_g, d + o_lg, B * m * 8, cudaMemcpyDeviceToHost, st));
+  if (lam_x && !m_lx) CU(cudaMemcpyAsync(lam_x, d + o_lx, B * n * 8, cudaMemcpyDeviceToHost, st));
+  if (f && !m_f) CU(cudaMemcpyAsync(f, d + o_f, B * 8, cudaMemcpyDeviceToHost, st));
+  if (kkt_err && !m_k) CU(cudaMemcpyAsync(kkt_err, d + o_k, B * 8, cudaMemcpyDeviceToHost, st));
+  if (!m_it) CU(cudaMemcpyAsync(iters, d + o_it, B * 4, cudaMemcpyDeviceToHost, st));
+  if (!m_st) CU(cudaMemcpyAsync(status, d + o_st, B * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return BMPC_OK;
 }

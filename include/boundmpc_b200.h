@@ -84,7 +84,11 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
 
 /* Same call with HOST pointers (what a Python / ROS caller holds): copies x0 and p to the
  * device, solves, copies the results back and synchronises.  Device buffers are owned and
- * cached by the handle.  Any output pointer except x, iters, status may be NULL. */
+ * cached by the handle.  Any output pointer except x, iters, status may be NULL.
+ * A result buffer in page-locked host memory the device can address (cudaHostAlloc /
+ * cudaHostRegister, a pinned torch tensor) is written by the kernel directly, instance by
+ * instance as the solves end, instead of being copied after the launch (same results;
+ * BMPC_NO_ZERO_COPY=1 in the environment forces the copies). */
 int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g,
                           double* lam_g, double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err);
 

@@ -118,3 +118,29 @@ def test_two_pass_scheduling_is_bitwise_neutral(solver, monkeypatch):
     for k in ("x", "g", "lam_g", "lam_x", "f", "kkt", "iters", "status"):
         assert np.array_equal(a[k], b[k]), k
     assert (a["status"] == 0).all()
+
+
+def test_host_entry_writes_pinned_result_buffers_directly(solver, monkeypatch):
+    """bmpc_solve_batch_host with page-locked result buffers (written by the kernel, no copy after the launch) returns
+    bitwise the same as with pageable buffers (device buffers + copies), and as with BMPC_NO_ZERO_COPY=1."""
+    from boundmpc_b200 import batches
+    B = 300
+    x0, p = batches.make_batch(solver, ("exp1", "exp2"), 0, B, bound_scale=True)
+    ref = solver.solve_batch(x0, p)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        return t.numpy()
+    out = {k: pinned(v) for k, v in ref.items()}
+    for v in out.values():
+        v.fill(0)
+    res = solver.solve_batch(x0, p, out)
+    for k in ref:
+        assert res[k] is out[k]
+        np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
+    monkeypatch.setenv("BMPC_NO_ZERO_COPY", "1")
+    for v in out.values():
+        v.fill(0)
+    res = solver.solve_batch(x0, p, out)
+    for k in ref:
+        np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
