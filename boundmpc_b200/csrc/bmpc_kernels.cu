@@ -28,6 +28,9 @@ struct BatchIO {
   const double* x0; const double* p;
   double *x, *g, *lam_g, *lam_x, *f, *kkt;
   int32_t *iters, *status;
+  // host entry with page-locked inputs: device-addressable host copies of x0 / p; the CTA that starts an instance
+  // fetches its 7.5 KB into the device buffers x0 / p (which it owns until then) instead of a copy before the launch
+  const double* x0_src; const double* p_src;
 };
 
 #ifdef BMPC_TRACE
@@ -133,6 +136,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 #ifdef BMPC_TRACE
     if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 2 : 0)] = gtime();
 #endif
+    if (io.x0_src && mode != RUN_RESUME) {
+      // (loads in batches of four per thread: the reads cross PCIe, one round trip per batch)
+      double* dst[2] = {const_cast<double*>(ii.x0), const_cast<double*>(ii.p)};
+      const double* src[2] = {io.x0_src + (size_t)b * C.n, io.p_src + (size_t)b * C.np};
+      const int cnt[2] = {C.n, C.np};
+#pragma unroll 1
+      for (int a = 0; a < 2; a++)
+#pragma unroll 1
+        for (int i0 = threadIdx.x; i0 < cnt[a]; i0 += 4 * blockDim.x) {
+          double v[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int i = i0 + q * blockDim.x; v[q] = i < cnt[a] ? src[a][i] : 0.0; }
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int i = i0 + q * blockDim.x; if (i < cnt[a]) dst[a][i] = v[q]; }
+        }
+      __syncthreads();
+    }
     const int rc = solve_instance(cx, C, W, S, ii, mode, M.save ? M.save + (size_t)b * M.save_stride : nullptr);
 #ifdef BMPC_TRACE
     if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 3 : 1)] = gtime() | (rc == PARKED_HARD ? 1ull : 0ull);
@@ -512,8 +532,16 @@ int bmpc_fp64_peak(bmpc_handle* h, int32_t kind, double* flops_per_s) {
   return BMPC_OK;
 }
 
+static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+                            double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err, void* workspace, void* cuda_stream,
+                            const double* x0_src, const double* p_src);
 int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
                      double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err, void* workspace, void* cuda_stream) {
+  return solve_batch_impl(h, batch, x0, p, x, g, lam_g, lam_x, f, iters, status, kkt_err, workspace, cuda_stream, nullptr, nullptr);
+}
+static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
+                            double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err, void* workspace, void* cuda_stream,
+                            const double* x0_src, const double* p_src) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch: null handle");
   if (batch < 0 || !x0 || !p || !x || !g || !lam_g || !lam_x || !f || !iters || !status || !kkt_err || !workspace)
     return fail(BMPC_E_INVALID, "bmpc_solve_batch: null buffer");
@@ -535,7 +563,7 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
     M.two_pass = 1;
     CU(cudaMemsetAsync(M.list_h, 0xFF, (size_t)2 * batch * sizeof(int), st));
   }
-  BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status};
+  BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status, x0_src, p_src};
   const int v = (h->variant_lat >= 0 && batch <= h->sms) ? h->variant_lat : h->variant;
   kVariants[v].fn<<<grid, kVariants[v].threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, M);
   CU(cudaGetLastError());
@@ -561,12 +589,12 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   if (rc) return rc;
   char* d = (char*)h->dbuf;
   cudaStream_t st = h->stream;
-  CU(cudaMemcpyAsync(d + o_x0, x0, B * n * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
   // Results.  A result buffer in page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister,
   // e.g. a pinned torch tensor) is written by the kernel itself: every instance stores its 14 KB of results when its
   // solve ends, so the transfer runs under the launch instead of after it (114 MB per 8,192 instances otherwise).
-  // Anything else gets a device buffer and a copy.  (Inputs are always copied: p is read throughout the solve.)
+  // Anything else gets a device buffer and a copy.  Page-locked inputs are handled the same way from the other side:
+  // the CTA that starts an instance fetches its x0 / p (7.5 KB) into the device buffers, which it then reads throughout
+  // the solve; pageable inputs are copied before the launch.
   auto mapped = [&](const void* host) -> void* {
     if (!host || getenv("BMPC_NO_ZERO_COPY")) return nullptr;
     cudaPointerAttributes a;
@@ -575,11 +603,17 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   };
   void *m_x = mapped(x), *m_g = mapped(g), *m_lg = mapped(lam_g), *m_lx = mapped(lam_x), *m_f = mapped(f), *m_k = mapped(kkt_err),
        *m_it = mapped(iters), *m_st = mapped(status);
-  rc = bmpc_solve_batch(h, batch, (double*)(d + o_x0), (double*)(d + o_p), m_x ? (double*)m_x : (double*)(d + o_x),
+  const void *s_x0 = mapped(x0), *s_p = mapped(p);
+  if (!s_x0 || !s_p) {
+    s_x0 = s_p = nullptr;
+    CU(cudaMemcpyAsync(d + o_x0, x0, B * n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
+  }
+  rc = solve_batch_impl(h, batch, (double*)(d + o_x0), (double*)(d + o_p), m_x ? (double*)m_x : (double*)(d + o_x),
                         m_g ? (double*)m_g : (double*)(d + o_g), m_lg ? (double*)m_lg : (double*)(d + o_lg),
                         m_lx ? (double*)m_lx : (double*)(d + o_lx), m_f ? (double*)m_f : (double*)(d + o_f),
                         m_it ? (int32_t*)m_it : (int32_t*)(d + o_it), m_st ? (int32_t*)m_st : (int32_t*)(d + o_st),
-                        m_k ? (double*)m_k : (double*)(d + o_k), d + o_ws, st);
+                        m_k ? (double*)m_k : (double*)(d + o_k), d + o_ws, st, (const double*)s_x0, (const double*)s_p);
   if (rc) return rc;
   if (!m_x) CU(cudaMemcpyAsync(x, d + o_x, B * n * 8, cudaMemcpyDeviceToHost, st));
   if (g && !m_g) CU(cudaMemcpyAsync(g, d + o_g, B * m * 8, cudaMemcpyDeviceToHost, st));

@@ -1,10 +1,10 @@
 #!/bin/bash
-# GPU tests, then the default bench with and without the zero-copy result path of the host entry.
+# GPU tests, then the default bench with and without the zero-copy paths of the host entry.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
 for z in 1 0; do
   if [ $z = 1 ]; then export BMPC_NO_ZERO_COPY=1; else unset BMPC_NO_ZERO_COPY; fi
-  timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_zc$z.json 2> gpurun_out/bench_zc$z.err
+  timeout 300 python bench.py $BENCH_FLAGS > gpurun_out/bench_zc$z.json 2> gpurun_out/bench_zc$z.err
   python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_zc$z.json"))

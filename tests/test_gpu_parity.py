@@ -120,9 +120,10 @@ def test_two_pass_scheduling_is_bitwise_neutral(solver, monkeypatch):
     assert (a["status"] == 0).all()
 
 
-def test_host_entry_writes_pinned_result_buffers_directly(solver, monkeypatch):
-    """bmpc_solve_batch_host with page-locked result buffers (written by the kernel, no copy after the launch) returns
-    bitwise the same as with pageable buffers (device buffers + copies), and as with BMPC_NO_ZERO_COPY=1."""
+def test_host_entry_with_page_locked_buffers(solver, monkeypatch):
+    """bmpc_solve_batch_host with page-locked buffers (results written by the kernel, inputs fetched by it: no copies
+    around the launch) returns bitwise the same as with pageable buffers (device buffers + copies), and as with
+    BMPC_NO_ZERO_COPY=1."""
     from boundmpc_b200 import batches
     B = 300
     x0, p = batches.make_batch(solver, ("exp1", "exp2"), 0, B, bound_scale=True)
@@ -138,9 +139,20 @@ def test_host_entry_writes_pinned_result_buffers_directly(solver, monkeypatch):
     for k in ref:
         assert res[k] is out[k]
         np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
+    # page-locked inputs too: fetched by the CTA that starts an instance instead of copied before the launch
+    x0p, pp = pinned(x0), pinned(p)
+    x0p[:], pp[:] = x0, p
+    for v in out.values():
+        v.fill(0)
+    res = solver.solve_batch(x0p, pp, out)
+    for k in ref:
+        np.testing.assert_array_equal(res[k], ref[k], err_msg=k + " (pinned inputs)")
+    res = solver.solve_batch(x0p, pp)          # pinned inputs, pageable results
+    for k in ref:
+        np.testing.assert_array_equal(res[k], ref[k], err_msg=k + " (pinned inputs only)")
     monkeypatch.setenv("BMPC_NO_ZERO_COPY", "1")
     for v in out.values():
         v.fill(0)
-    res = solver.solve_batch(x0, p, out)
+    res = solver.solve_batch(x0p, pp, out)
     for k in ref:
         np.testing.assert_array_equal(res[k], ref[k], err_msg=k)
