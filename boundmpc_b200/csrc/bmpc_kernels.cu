@@ -388,16 +388,26 @@ struct bmpc_handle {
   int64_t launches;
   // cached device buffers of the host-pointer entry points
   void* dbuf; size_t dbuf_bytes;
+  void* pin; size_t pin_bytes;      // page-locked staging area of the host entry for small pageable batches
   cudaStream_t stream;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int BMPC_STAGE_MAX = 64;   // largest pageable batch the host entry stages through its page-locked area
 
 static int ensure_dbuf(bmpc_handle* h, size_t bytes) {
   if (h->dbuf_bytes >= bytes) return BMPC_OK;
   if (h->dbuf) { cudaFree(h->dbuf); h->dbuf = nullptr; h->dbuf_bytes = 0; }
   CU(cudaMalloc(&h->dbuf, bytes));
   h->dbuf_bytes = bytes;
+  return BMPC_OK;
+}
+
+static int ensure_pin(bmpc_handle* h, size_t bytes) {
+  if (h->pin_bytes >= bytes) return BMPC_OK;
+  if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
+  CU(cudaHostAlloc(&h->pin, bytes, cudaHostAllocDefault));
+  h->pin_bytes = bytes;
   return BMPC_OK;
 }
 
@@ -456,6 +466,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
   h->launches = 0;
   h->dbuf = nullptr; h->dbuf_bytes = 0;
+  h->pin = nullptr; h->pin_bytes = 0;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   *out = h;
@@ -466,6 +477,7 @@ void bmpc_destroy(bmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dbuf) cudaFree(h->dbuf);
+  if (h->pin) cudaFreeHost(h->pin);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -572,12 +584,47 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
 }
 
 
+static bool is_mapped_host(const void* ptr) {
+  cudaPointerAttributes a;
+  if (!ptr) return false;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g, double* lam_g,
                           double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null handle");
   if (batch < 0 || !x0 || !p || !x || !iters || !status) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null buffer");
   if (batch == 0) return BMPC_OK;
   CU(cudaSetDevice(h->device));
+  // Small batches in pageable memory (the single MPC step of a Python / ROS caller): ten small copies around the launch
+  // cost more than the transfers themselves.  They are staged through a page-locked area of the handle, which the
+  // kernel reads and writes itself (see below): two host memcpys and one launch.
+  if (batch <= BMPC_STAGE_MAX && !getenv("BMPC_NO_ZERO_COPY") && !(is_mapped_host(x0) && is_mapped_host(x))) {
+    const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_x0 = take(B * n * 8), o_p = take(B * np * 8), o_x = take(B * n * 8), o_g = take(B * m * 8), o_lg = take(B * m * 8),
+                 o_lx = take(B * n * 8), o_f = take(B * 8), o_k = take(B * 8), o_it = take(B * 4), o_st = take(B * 4);
+    int rc = ensure_pin(h, off);
+    if (rc) return rc;
+    char* q = (char*)h->pin;
+    memcpy(q + o_x0, x0, B * n * 8);
+    memcpy(q + o_p, p, B * np * 8);
+    rc = bmpc_solve_batch_host(h, batch, (const double*)(q + o_x0), (const double*)(q + o_p), (double*)(q + o_x), (double*)(q + o_g),
+                               (double*)(q + o_lg), (double*)(q + o_lx), (double*)(q + o_f), (int32_t*)(q + o_it), (int32_t*)(q + o_st),
+                               (double*)(q + o_k));
+    if (rc) return rc;
+    memcpy(x, q + o_x, B * n * 8);
+    if (g) memcpy(g, q + o_g, B * m * 8);
+    if (lam_g) memcpy(lam_g, q + o_lg, B * m * 8);
+    if (lam_x) memcpy(lam_x, q + o_lx, B * n * 8);
+    if (f) memcpy(f, q + o_f, B * 8);
+    if (kkt_err) memcpy(kkt_err, q + o_k, B * 8);
+    memcpy(iters, q + o_it, B * 4);
+    memcpy(status, q + o_st, B * 4);
+    return BMPC_OK;
+  }
   const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np;
   size_t wsb = 0;
   bmpc_workspace_bytes(h, batch, &wsb);

@@ -88,8 +88,9 @@ int bmpc_solve_batch(bmpc_handle* h, int32_t batch, const double* x0, const doub
  * A result buffer in page-locked host memory the device can address (cudaHostAlloc /
  * cudaHostRegister, a pinned torch tensor) is written by the kernel directly, instance by
  * instance as the solves end, instead of being copied after the launch; page-locked x0 / p
- * are fetched by the kernel when an instance starts instead of being copied before it (same
- * results; BMPC_NO_ZERO_COPY=1 in the environment forces the copies). */
+ * are fetched by the kernel when an instance starts instead of being copied before it; batches
+ * of at most 64 instances in pageable memory are staged through a page-locked area owned by
+ * the handle (same results; BMPC_NO_ZERO_COPY=1 in the environment forces the copies). */
 int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const double* p, double* x, double* g,
                           double* lam_g, double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt_err);
 
