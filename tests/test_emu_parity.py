@@ -52,6 +52,23 @@ def test_same_iterates_as_oracle():
         assert np.abs(ro["x"] - re["x"][0]).max() < 1e-8
 
 
+def test_doubled_horizon_same_iterates_as_oracle():
+    """N = 20 (BASELINE configs[3]) takes the other branches of the kernel source: iterate and step vectors in the global
+    workspace instead of shared memory, and an adjoint sweep whose staged kinematic columns cover only the last 12
+    stages (the earlier ones are read from the stage records).  Starts: golden N = 10 warm starts with the last stage
+    repeated."""
+    S = load("seq_exp1.npz")
+    for i in (0, 4, 9):
+        x0 = S["x0"][i].reshape(10, 44)
+        x20 = np.concatenate([x0, np.repeat(x0[-1:], 10, axis=0)]).ravel()
+        ro = O.solve(x20, S["p"][i], N=20, tol=1e-9)
+        re = emu.solve(x20, S["p"][i], N=20, tol=1e-9)
+        assert ro["status"] == 0 and re["status"][0] == 0
+        assert ro["iters"] == re["iters"][0]
+        assert np.abs(ro["x"] - re["x"][0]).max() < 1e-7
+        assert abs(ro["f"] - re["f"][0]) < 1e-9 * abs(ro["f"])
+
+
 def test_park_and_resume_is_bitwise_neutral():
     """Two-pass scheduling of k_solve: parking an instance after its first slice and resuming it later (other
     instances in between, same scratch) must not change a single bit of the result."""
