@@ -7,8 +7,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libboundmpc_b200.so")
 SOURCES = ["bmpc_kernels.cu"]
-HEADERS = ["bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h",
-           os.path.join("..", "..", "include", "boundmpc_b200.h")]
+import glob
+
+
+def _headers():
+    """Everything the translation unit can include, plus this file (the flags are part of the build)."""
+    return (sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")))
+            + [os.path.join(HERE, "..", "include", "boundmpc_b200.h"), os.path.abspath(__file__)])
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared", "-diag-suppress", "128"]
 
@@ -17,7 +22,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, s) for s in SOURCES] + _headers())
 
 
 TIMING_LIB = os.path.join(HERE, "libboundmpc_b200_timing.so")   # development build with per-phase cycle counters

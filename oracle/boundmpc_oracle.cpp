@@ -24,6 +24,8 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+static std::atomic<long> g_soc_solves{0}, g_soc_accepted{0};
 #include "ocp_model.hpp"
 
 using namespace orc;
@@ -298,10 +300,16 @@ struct Opts {
   int max_iter = 500;
   double mu_init = 1e-3;      // level of Ipopt's warm_start_mult_bound_push (see bmpc_host.h make_config)
   double bound_push = 1e-3;   // Ipopt warm_start_bound_push / warm_start_slack_bound_push
-  double kappa_eps = 10, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100;
+  double kappa_eps = 1000, kappa_mu = 0.1, theta_mu = 2.0, tau_min = 0.99, s_max = 100;   // fast monotone schedule (bmpc_host.h make_config)
   double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta_sw = 1.0;
   int verbose = 0;
   double diverge_tol = 1e7;   // dual infeasibility beyond which the multipliers are taken to diverge (locally infeasible instance)
+  int mu_strategy = 3;        // 0: monotone; 3 (default, = the CUDA path): monotone + kkt-error progress test with re-centring;
+                              // experiments: 1 adaptive with the LOQO oracle, 2 adaptive with a quality-function oracle
+  int zinit = 0;              // 0: z = mu_init / slack, 1: z = mu_init (Ipopt warm_start_mult_bound_push)
+  double mu_min = 1e-11, mu_max_fact = 1e3;
+  double rz_kappa = 0; int red_iters = 3; int single_dec = 1; int max_soc = 0;
+  double boost_thr = 0, boost_fac = 10, boost_cap = 1.0; int boost_hold = 0;
 };
 
 struct Ipm {
@@ -315,6 +323,8 @@ struct Ipm {
   std::vector<double> lbx, ubx;
   Eval E;
   double mu, delta_w_last = 0;
+  const double* soc_c = nullptr; const double* soc_d = nullptr;   // second-order correction: residuals replacing c [NE N] and d + s [ND N]
+  double* trace = nullptr; int trace_cap = 0;   // optional per-iteration log: e0, mu, alpha_pr_max, alpha, theta, dw
   std::vector<std::pair<double, double>> filter;
   // Riccati storage
   std::vector<double> Wt, gh, Kk, kk, Pn, pn;
@@ -396,7 +406,14 @@ struct Ipm {
   }
 
   // Solve the condensed KKT system by Riccati; returns false if some Q_uu is not PD.
-  bool riccati(double delta_w) {
+  // right-hand side: gh = ga * (mu-free part) + gc * (coefficient of mu), equality residual scaled by cs
+  // (full step: ga = 1, gc = mu, cs = 1; affine-scaling step: 1, 0, 1; centring step: 0, 1, 0)
+  bool riccati(double delta_w, double ga = 1.0, double gc = -1.0, double cs = 1.0) {
+    if (gc < 0) gc = mu;
+    std::vector<double> csc(NG * N);
+    for (int i = 0; i < NG * N; i++) csc[i] = cs * E.g[i];
+    if (soc_c) for (int k = 0; k < N; k++) for (int i = 0; i < NE; i++) csc[NG * k + i] = cs * soc_c[NE * k + i];
+    auto c_ = [&](int k) { return &csc[NG * k]; };
     // W~ and g^ -------------------------------------------------------
     for (int k = 0; k < N; k++) {
       double* W = &Wt[k * NX * NX];
@@ -404,16 +421,16 @@ struct Ipm {
       const double* Jd = &E.Jd[k * ND * NX];
       for (int i = 0; i < NX; i++) {
         int gi = NX * k + i;
-        double sig = delta_w, gb = E.gradf[gi];
-        if (std::isfinite(lbx[gi])) { double sl = x[gi] - lbx[gi]; sig += zL[gi] / sl; gb -= mu / sl; }
-        if (std::isfinite(ubx[gi])) { double su = ubx[gi] - x[gi]; sig += zU[gi] / su; gb += mu / su; }
+        double sig = delta_w, gb = ga * E.gradf[gi];
+        if (std::isfinite(lbx[gi])) { double sl = x[gi] - lbx[gi]; sig += zL[gi] / sl; gb -= gc / sl; }
+        if (std::isfinite(ubx[gi])) { double su = ubx[gi] - x[gi]; sig += zU[gi] / su; gb += gc / su; }
         W[i * NX + i] += sig;
         gh[gi] = gb;
       }
       for (int r = 0; r < ND; r++) {
         double sv = s[ND * k + r], zv = zs[ND * k + r];
-        double Sig = zv / sv, rd = d_(k)[r] + sv;
-        double coef = mu / sv + Sig * rd;
+        double Sig = zv / sv, rd = soc_d ? soc_d[ND * k + r] : d_(k)[r] + sv;
+        double coef = gc / sv + ga * Sig * rd;
         for (int i = 0; i < NX; i++) {
           double ji = Jd[r * NX + i];
           if (ji == 0.0) continue;
@@ -585,16 +602,22 @@ struct Ipm {
       eval_values(P, x.data(), p, f, g.data(), d.data());
       for (int i = 0; i < ni; i++) s[i] = std::max(-d[i], o.bound_push);
     }
-    for (int i = 0; i < ni; i++) zs[i] = mu / s[i];
+    for (int i = 0; i < ni; i++) zs[i] = o.zinit ? mu : mu / s[i];
     for (int i = 0; i < n; i++) {
-      zL[i] = std::isfinite(lbx[i]) ? mu / (x[i] - lbx[i]) : 0.0;
-      zU[i] = std::isfinite(ubx[i]) ? mu / (ubx[i] - x[i]) : 0.0;
+      zL[i] = std::isfinite(lbx[i]) ? (o.zinit ? mu : mu / (x[i] - lbx[i])) : 0.0;
+      zU[i] = std::isfinite(ubx[i]) ? (o.zinit ? mu : mu / (ubx[i] - x[i])) : 0.0;
     }
     filter.clear();
     double theta0 = -1, theta_max = 0, theta_min = 0;
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
     int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
+    bool free_mode = true, ls_skipped = false, continue_flag = false;
+    int n_soc = 0;
+    double qf_avg = 0, qf_d = 0, qf_p = 0;
+    int boost_wait = 0;
+    double mu_max = -1;
+    std::vector<double> refs;
     for (;; it++) {
       pack_lam();
       eval_full(P, x.data(), p, lam.data(), E, true);
@@ -605,46 +628,168 @@ struct Ipm {
       if (e0 <= o.tol) { status = 0; break; }
       if (it >= o.max_iter) { status = 1; break; }
       if (parts[0] > o.diverge_tol) { status = 5; break; }
-      // barrier parameter (monotone Fiacco-McCormick, Ipopt eq. (7))
-      bool mu_changed = false;
-      while (mu > o.tol / 10 && kkt_error(mu) <= o.kappa_eps * mu) {
-        mu = std::max(o.tol / 10, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
-        mu_changed = true;
+      // barrier parameter
+      if (o.mu_strategy == 0 || o.mu_strategy == 3) {
+        // monotone Fiacco-McCormick, Ipopt eq. (7)
+        bool mu_changed = false;
+        while (mu > o.tol / 10 && kkt_error(mu) <= o.kappa_eps * mu) {
+          mu = std::max(o.tol / 10, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
+          mu_changed = true;
+          if (o.single_dec) break;
+        }
+        if (mu_changed) { filter.clear(); refs.clear(); }
+        if (o.mu_strategy == 3) {
+          // progress monitor (Ipopt's kkt-error globalisation test, adaptive_mu_kkterror_red_iters = 4): when the optimality
+          // error has not improved on any of the last four iterates the iteration is crawling along the boundary
+          // (fraction-to-the-boundary cuts); re-centre at a larger barrier parameter
+          double parts2[3];
+          const double qf = kkt_error(0.0, parts2);
+          bool suff = true;
+          if ((int)refs.size() >= o.red_iters) { suff = false; for (double r : refs) if (qf <= 0.9999 * r) suff = true; }
+          if (suff) { if ((int)refs.size() >= o.red_iters) refs.erase(refs.begin()); refs.push_back(qf); }
+          else if (mu < o.boost_cap) {
+            mu = std::min(o.boost_cap, o.boost_fac * mu);
+            filter.clear(); refs.clear();
+            if (o.verbose) printf("      no progress: mu -> %.3e\n", mu);
+          }
+        }
+      } else {
+        // adaptive: Ipopt's AdaptiveMuUpdate with the LOQO oracle and kkt-error globalisation
+        double csum = 0, cmin = 1e300, q_d = 0, q_p = 0, q_c = 0; int nc = 0;
+        for (int i = 0; i < ni; i++) { double c = s[i] * zs[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
+        for (int i = 0; i < n; i++) {
+          if (std::isfinite(lbx[i])) { double c = (x[i] - lbx[i]) * zL[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
+          if (std::isfinite(ubx[i])) { double c = (ubx[i] - x[i]) * zU[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
+        }
+        const double avg = csum / nc, xi = cmin / avg;
+        {
+          std::vector<double> r; dual_residual(y, zs, r);
+          for (int i = 0; i < n; i++) q_d += r[i] * r[i];
+          for (int k = 0; k < N; k++) {
+            for (int i = 0; i < NE; i++) q_p += E.g[NG * k + i] * E.g[NG * k + i];
+            for (int i = 0; i < ND; i++) { double v = E.d[ND * k + i] + s[ND * k + i]; q_p += v * v; }
+          }
+        }
+        const double qf = q_d / n + q_p / (ne + ni) + q_c / nc;
+        qf_avg = avg; qf_d = q_d / n; qf_p = q_p / (ne + ni);
+        if (mu_max < 0) mu_max = o.mu_max_fact * avg;
+        bool suff = true;
+        if ((int)refs.size() >= 4) { suff = false; for (double r : refs) if (qf <= 0.9999 * r) suff = true; }
+        auto remember = [&]() { if ((int)refs.size() >= 4) refs.erase(refs.begin()); refs.push_back(qf); };
+        if (!free_mode) {
+          if (suff) { free_mode = true; remember(); }
+          else if (kkt_error(mu) <= o.kappa_eps * mu) {
+            mu = std::max(o.mu_min, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
+            filter.clear();
+          }
+        } else {
+          if (ls_skipped) suff = false;
+          if (suff) remember();
+          else { free_mode = false; mu = std::min(mu_max, std::max(o.mu_min, 0.8 * avg)); filter.clear(); }
+        }
+        if (free_mode && o.mu_strategy == 1) {
+          const double fac = 0.05 * (1 - xi) / xi;
+          const double sigma = 0.1 * std::pow(std::min(fac, 2.0), 3);
+          mu = std::min(mu_max, std::max(o.mu_min, sigma * avg));
+          filter.clear();
+        }
+        if (o.verbose) printf("      adaptive: free %d avg %.3e xi %.3e qf %.3e -> mu %.3e\n", (int)free_mode, avg, xi, qf, mu);
       }
-      if (mu_changed) filter.clear();
+      if (o.rz_kappa > 0) {
+        // infeasibility-aware floor of the barrier parameter: a violated inequality row (d + s > 0) whose multiplier has grown
+        // pins its slack at zero, and the fraction-to-the-boundary rule then cuts every step to a crawl; re-centre so that the
+        // barrier keeps that slack away from zero while the row is being made feasible
+        double mrz = 0;
+        for (int i = 0; i < ni; i++) mrz = std::max(mrz, (E.d[i] + s[i]) * zs[i]);
+        if (o.rz_kappa * mrz > mu) {
+          mu = std::min(o.boost_cap, o.rz_kappa * mrz); filter.clear();
+          if (o.verbose) printf("      rz floor: mu -> %.3e\n", mu);
+        }
+      }
       double th_cur = theta(E.g.data(), E.d.data(), s);
       if (theta0 < 0) { theta0 = th_cur; theta_max = 1e4 * std::max(1.0, theta0); theta_min = 1e-4 * std::max(1.0, theta0); }
       // search direction with inertia correction
       double dw = 0;
-      bool ok = riccati(0.0);
-      if (!ok) {
-        dw = delta_w_last == 0 ? 1e-4 : std::max(1e-20, delta_w_last / 3);
-        for (int tries = 0; tries < 60; tries++) {
-          ok = riccati(dw);
-          if (ok) break;
-          dw *= (delta_w_last == 0 ? 100 : 8);
-          if (dw > 1e40) break;
+      auto factor_solve = [&](double ga, double gc, double cs) -> bool {
+        bool ok = riccati(dw, ga, gc, cs);
+        if (!ok) {
+          dw = delta_w_last == 0 ? 1e-4 : std::max(1e-20, delta_w_last / 3);
+          for (int tries = 0; tries < 60; tries++) {
+            ok = riccati(dw, ga, gc, cs);
+            if (ok) break;
+            dw *= (delta_w_last == 0 ? 100 : 8);
+            if (dw > 1e40) break;
+          }
+          if (ok) delta_w_last = dw;
         }
-        if (!ok) { status = 3; break; }
-        delta_w_last = dw;
+        return ok;
+      };
+      auto rest_of_step = [&](double ga, double gc) {   // ds, dzs, dzL, dzU from dx for the right-hand side (ga, gc)
+        for (int k = 0; k < N; k++) {
+          const double* Jd = &E.Jd[k * ND * NX];
+          for (int r = 0; r < ND; r++) {
+            double jd = 0;
+            for (int j = 0; j < NX; j++) jd += Jd[r * NX + j] * dx[NX * k + j];
+            int i = ND * k + r;
+            ds[i] = -ga * (soc_d ? soc_d[i] : d_(k)[r] + s[i]) - jd;
+            dzs[i] = gc / s[i] - ga * zs[i] - zs[i] / s[i] * ds[i];
+          }
+        }
+        for (int i = 0; i < n; i++) {
+          dzL[i] = dzU[i] = 0;
+          if (std::isfinite(lbx[i])) { double sl = x[i] - lbx[i]; dzL[i] = gc / sl - ga * zL[i] - zL[i] / sl * dx[i]; }
+          if (std::isfinite(ubx[i])) { double su = ubx[i] - x[i]; dzU[i] = gc / su - ga * zU[i] + zU[i] / su * dx[i]; }
+        }
+      };
+      if (o.mu_strategy == 2 && free_mode) {
+        // quality-function oracle (Ipopt's QualityFunctionMuOracle): the step is affine in mu, step(mu) = step_a + mu step_c
+        if (!factor_solve(1, 0, 1)) { status = 3; break; }
+        rest_of_step(1, 0);
+        std::vector<double> ax = dx, as = ds, ay = ynew, azs = dzs, azL = dzL, azU = dzU;
+        if (!riccati(dw, 0, 1, 0)) { status = 3; break; }
+        rest_of_step(0, 1);
+        std::vector<double> cx = dx, cs_ = ds, cy = ynew, czs = dzs, czL = dzL, czU = dzU;
+        const double avg = qf_avg;
+        auto qf = [&](double muc) {
+          const double tauq = std::max(o.tau_min, 1 - muc);
+          double ap = 1, ad = 1;
+          for (int i = 0; i < ni; i++) {
+            double d1 = as[i] + muc * cs_[i], d2 = azs[i] + muc * czs[i];
+            if (d1 < 0) ap = std::min(ap, -tauq * s[i] / d1);
+            if (d2 < 0) ad = std::min(ad, -tauq * zs[i] / d2);
+          }
+          for (int i = 0; i < n; i++) {
+            double d1 = ax[i] + muc * cx[i];
+            if (std::isfinite(lbx[i])) { double d2 = azL[i] + muc * czL[i]; if (d1 < 0) ap = std::min(ap, -tauq * (x[i] - lbx[i]) / d1); if (d2 < 0) ad = std::min(ad, -tauq * zL[i] / d2); }
+            if (std::isfinite(ubx[i])) { double d2 = azU[i] + muc * czU[i]; if (d1 > 0) ap = std::min(ap, tauq * (ubx[i] - x[i]) / d1); if (d2 < 0) ad = std::min(ad, -tauq * zU[i] / d2); }
+          }
+          double qc = 0; int nc = 0;
+          for (int i = 0; i < ni; i++) { double v = (s[i] + ap * (as[i] + muc * cs_[i])) * (zs[i] + ad * (azs[i] + muc * czs[i])); qc += v * v; nc++; }
+          for (int i = 0; i < n; i++) {
+            double d1 = ax[i] + muc * cx[i];
+            if (std::isfinite(lbx[i])) { double v = (x[i] - lbx[i] + ap * d1) * (zL[i] + ad * (azL[i] + muc * czL[i])); qc += v * v; nc++; }
+            if (std::isfinite(ubx[i])) { double v = (ubx[i] - x[i] - ap * d1) * (zU[i] + ad * (azU[i] + muc * czU[i])); qc += v * v; nc++; }
+          }
+          return (1 - ad) * (1 - ad) * qf_d + (1 - ap) * (1 - ap) * qf_p + qc / nc;
+        };
+        double best = 1e300, bs = 1;
+        for (double lg = -6; lg <= 2.001; lg += 0.5) {
+          const double sg = std::pow(10.0, lg);
+          const double muc = std::min(mu_max, std::max(o.mu_min, sg * avg));
+          const double q = qf(muc);
+          if (q < best) { best = q; bs = muc; }
+        }
+        mu = bs;
+        filter.clear();
+        if (o.verbose) printf("      qf oracle: avg %.3e -> mu %.3e (sigma %.3g)\n", avg, mu, mu / avg);
+        for (int i = 0; i < n; i++) { dx[i] = ax[i] + mu * cx[i]; dzL[i] = azL[i] + mu * czL[i]; dzU[i] = azU[i] + mu * czU[i]; }
+        for (int i = 0; i < ni; i++) { ds[i] = as[i] + mu * cs_[i]; dzs[i] = azs[i] + mu * czs[i]; }
+        for (int i = 0; i < ne; i++) ynew[i] = ay[i] + mu * cy[i];
+      } else {
+        if (!factor_solve(1, mu, 1)) { status = 3; break; }
+        rest_of_step(1, mu);
       }
       if (o.verbose > 1) printf("      delta_w %.1e lin_res %.2e\n", dw, lin_residual());
-      // remaining step components
-      for (int k = 0; k < N; k++) {
-        const double* Jd = &E.Jd[k * ND * NX];
-        for (int r = 0; r < ND; r++) {
-          double jd = 0;
-          for (int j = 0; j < NX; j++) jd += Jd[r * NX + j] * dx[NX * k + j];
-          int i = ND * k + r;
-          ds[i] = -(d_(k)[r] + s[i]) - jd;
-          dzs[i] = mu / s[i] - zs[i] - zs[i] / s[i] * ds[i];
-        }
-      }
-      for (int i = 0; i < n; i++) {
-        dzL[i] = dzU[i] = 0;
-        if (std::isfinite(lbx[i])) { double sl = x[i] - lbx[i]; dzL[i] = mu / sl - zL[i] - zL[i] / sl * dx[i]; }
-        if (std::isfinite(ubx[i])) { double su = ubx[i] - x[i]; dzU[i] = mu / su - zU[i] + zU[i] / su * dx[i]; }
-      }
       // fraction to the boundary
       double tau = std::max(o.tau_min, 1 - mu), apr = 1, adu = 1;
       for (int i = 0; i < ni; i++) {
@@ -678,6 +823,25 @@ struct Ipm {
       // of iterations while the dual infeasibility stays above tol); Newton's full step is taken instead, as Ipopt
       // does for its "tiny steps"
       const bool flat = th_cur <= 1e-10 && std::fabs(dphi) <= 1e-10 * std::max(1.0, std::fabs(phi_cur));
+      // acceptance of a trial point (theta, phi) for a step of length a_sw along the search direction
+      // (Waechter & Biegler 2006, Alg. A, steps A-5.3 / A-5.4), with Ipopt's round-off allowance (Compare_le: lhs - rhs <=
+      // 10 eps |reference value|): close to the solution the decrease conditions are decided by rounding noise and a
+      // strict test sends the iteration into dozens of useless backtracking steps
+      auto acceptable = [&](double th, double ph, double a_sw, bool& ft_out) -> bool {
+        if (!std::isfinite(th) || !std::isfinite(ph) || th > theta_max) return false;
+        if (flat) { ft_out = true; return true; }
+        for (auto& fe : filter)
+          if (!(th < fe.first || ph < fe.second)) return false;
+        const bool sw = dphi < 0 && a_sw * std::pow(-dphi, o.s_phi) > o.delta_sw * std::pow(th_cur, o.s_theta);
+        const double ro = 10 * 2.220446049250313e-16;
+        if (th_cur <= theta_min && sw) {
+          if (ph - phi_cur - o.eta_phi * a_sw * dphi <= ro * std::fabs(phi_cur)) { ft_out = true; return true; }
+        } else {
+          if (th - (1 - o.gamma_theta) * th_cur <= ro * std::fabs(th_cur) ||
+              ph - phi_cur + o.gamma_phi * th_cur <= ro * std::fabs(phi_cur)) { ft_out = false; return true; }
+        }
+        return false;
+      };
       for (int ls = 0; ls < 40; ls++, alpha *= 0.5) {
         for (int i = 0; i < n; i++) xt[i] = x[i] + alpha * dx[i];
         for (int i = 0; i < ni; i++) st[i] = s[i] + alpha * ds[i];
@@ -685,29 +849,55 @@ struct Ipm {
         eval_values(P, xt.data(), p, ft, gt.data(), dt_.data());
         th_t = theta(gt.data(), dt_.data(), st);
         ph_t = barrier_phi(ft, xt, st);
-        if (!std::isfinite(th_t) || !std::isfinite(ph_t) || th_t > theta_max) continue;
-        if (flat) { accepted = true; ftype = true; break; }
-        bool filt_ok = true;
-        for (auto& fe : filter)
-          if (!(th_t < fe.first || ph_t < fe.second)) { filt_ok = false; break; }
-        if (!filt_ok) continue;
-        bool sw = dphi < 0 && alpha * std::pow(-dphi, o.s_phi) > o.delta_sw * std::pow(th_cur, o.s_theta);
-        // comparisons with Ipopt's round-off allowance (Compare_le: lhs - rhs <= 10 eps |reference value|): close to the
-        // solution the decrease conditions are decided by rounding noise and a strict test sends the iteration
-        // into dozens of useless backtracking steps
-        const double ro = 10 * 2.220446049250313e-16;
-        if (th_cur <= theta_min && sw) {
-          if (ph_t - phi_cur - o.eta_phi * alpha * dphi <= ro * std::fabs(phi_cur)) { accepted = true; ftype = true; break; }
-        } else {
-          if (th_t - (1 - o.gamma_theta) * th_cur <= ro * std::fabs(th_cur) ||
-              ph_t - phi_cur + o.gamma_phi * th_cur <= ro * std::fabs(phi_cur)) { accepted = true; ftype = false; break; }
+        if (acceptable(th_t, ph_t, alpha, ftype)) { accepted = true; break; }
+        if (ls == 0 && o.max_soc > 0 && std::isfinite(th_t) && th_t >= th_cur) {
+          // ---- second-order correction (Waechter & Biegler 2006, Sec. 2.4; Ipopt max_soc = 4, kappa_soc = 0.99): the
+          // rejected full step has not reduced the constraint violation; re-solve with the residuals
+          // c_soc = alpha c(x_k) + c(x_k + alpha dx) and the factorisation of this iteration
+          std::vector<double> cs_c(ne), cs_d(ni), dx0 = dx, ds0 = ds, y0 = ynew, dzs0 = dzs, dzL0 = dzL, dzU0 = dzU;
+          for (int k = 0; k < N; k++) {
+            for (int i = 0; i < NE; i++) cs_c[NE * k + i] = alpha * E.g[NG * k + i] + gt[NG * k + i];
+            for (int i = 0; i < ND; i++) cs_d[ND * k + i] = alpha * (E.d[ND * k + i] + s[ND * k + i]) + dt_[ND * k + i] + st[ND * k + i];
+          }
+          double th_old = th_t;
+          bool soc_ok = false;
+          for (int q = 0; q < o.max_soc; q++) {
+            soc_c = cs_c.data(); soc_d = cs_d.data();
+            const bool okf = riccati(dw, 1, mu, 1);
+            g_soc_solves++;
+            if (okf) rest_of_step(1, mu);
+            soc_c = soc_d = nullptr;
+            if (!okf) break;
+            double a_soc = 1;
+            for (int i = 0; i < ni; i++) if (ds[i] < 0) a_soc = std::min(a_soc, -tau * s[i] / ds[i]);
+            for (int i = 0; i < n; i++) {
+              if (std::isfinite(lbx[i]) && dx[i] < 0) a_soc = std::min(a_soc, -tau * (x[i] - lbx[i]) / dx[i]);
+              if (std::isfinite(ubx[i]) && dx[i] > 0) a_soc = std::min(a_soc, tau * (ubx[i] - x[i]) / dx[i]);
+            }
+            for (int i = 0; i < n; i++) xt[i] = x[i] + a_soc * dx[i];
+            for (int i = 0; i < ni; i++) st[i] = s[i] + a_soc * ds[i];
+            eval_values(P, xt.data(), p, ft, gt.data(), dt_.data());
+            const double th_s = theta(gt.data(), dt_.data(), st), ph_s = barrier_phi(ft, xt, st);
+            if (o.verbose) printf("      soc %d: alpha %.3e theta %.3e -> %.3e (first trial %.3e)\n", q, a_soc, th_cur, th_s, th_t);
+            if (acceptable(th_s, ph_s, alpha, ftype)) { soc_ok = true; alpha = a_soc; th_t = th_s; ph_t = ph_s; break; }
+            if (!(th_s <= 0.99 * th_old)) break;
+            th_old = th_s;
+            for (int k = 0; k < N; k++) {
+              for (int i = 0; i < NE; i++) cs_c[NE * k + i] = a_soc * cs_c[NE * k + i] + gt[NG * k + i];
+              for (int i = 0; i < ND; i++) cs_d[ND * k + i] = a_soc * cs_d[ND * k + i] + dt_[ND * k + i] + st[ND * k + i];
+            }
+          }
+          if (soc_ok) { accepted = true; n_soc++; g_soc_accepted++; break; }
+          dx = dx0; ds = ds0; ynew = y0; dzs = dzs0; dzL = dzL0; dzU = dzU0;
         }
       }
+      ls_skipped = false;
       if (!accepted) {
         // no restoration phase: clear the filter and take the damped step that keeps the iterate interior
         filter.clear();
         alpha = apr * std::pow(0.5, 6);
         if (o.verbose) printf("      line search failed; damped step\n");
+        ls_skipped = true;
         if (++ls_fail > 8) { status = 2; break; }
       } else if (!ftype) {
         filter.push_back({(1 - o.gamma_theta) * th_cur, phi_cur - o.gamma_phi * th_cur});
@@ -718,6 +908,7 @@ struct Ipm {
         double dxm = 0; int idx = 0; for (int i = 0; i < n; i++) if (std::fabs(dx[i]) > dxm) { dxm = std::fabs(dx[i]); idx = i; }
         printf("      alpha_pr %.3e (max %.3e) alpha_du %.3e theta %.3e -> %.3e  phi %.6e -> %.6e dphi %.3e  zmax %.3e@%d,%d smin %.3e@%d,%d |dx| %.3e@%d,%d ftype %d filt %zu\n", alpha, apr, adu, th_cur, th_t, phi_cur, ph_t, dphi, zmax, iz / ND, iz % ND, smin, is / ND, is % ND, dxm, idx / 44, idx % 44, (int)ftype, filter.size());
       }
+      if (trace && it < trace_cap) { double* T = trace + 6 * it; T[0] = e0; T[1] = mu; T[2] = apr; T[3] = alpha; T[4] = th_cur; T[5] = dw; }
       for (int i = 0; i < n; i++) x[i] += alpha * dx[i];
       for (int i = 0; i < ni; i++) s[i] += alpha * ds[i];
       for (int i = 0; i < ne; i++) y[i] += alpha * (ynew[i] - y[i]);
@@ -730,6 +921,13 @@ struct Ipm {
         if (std::isfinite(lbx[i])) { double sl = x[i] - lbx[i]; zL[i] += adu * dzL[i]; zL[i] = std::max(std::min(zL[i], ks * mu / sl), mu / (ks * sl)); }
         if (std::isfinite(ubx[i])) { double su = ubx[i] - x[i]; zU[i] += adu * dzU[i]; zU[i] = std::max(std::min(zU[i], ks * mu / su), mu / (ks * su)); }
       }
+      if (o.boost_thr > 0 && apr < o.boost_thr && mu < o.boost_cap && boost_wait <= 0) {
+        // badly centred iterate: the fraction-to-the-boundary rule cuts Newton's step to a crawl; re-centre at a larger barrier parameter
+        mu = std::min(o.boost_cap, mu * o.boost_fac);
+        filter.clear();
+        boost_wait = o.boost_hold;
+        if (o.verbose) printf("      boost mu -> %.3e (apr %.3e)\n", mu, apr);
+      } else boost_wait--;
     }
     iters = it;
     return status;
@@ -838,6 +1036,7 @@ int orc_derivs_interval(int N, int S, double dt, const double* x, const double* 
   return 0;
 }
 
+static thread_local double* g_trace; static thread_local int g_trace_cap;
 // opts: [tol, max_iter, mu_init, bound_push, verbose]
 int orc_solve(int N, int S, double dt, const double* x0, const double* p, const double* opts,
               double* x, double* g, double* lam_g, double* lam_x, double* f, int* iters, double* kkt) {
@@ -850,7 +1049,21 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
     if (opts[3] > 0) o.bound_push = opts[3];
     o.verbose = (int)opts[4];
   }
+  if (const char* e = getenv("ORC_MU")) o.mu_strategy = atoi(e);
+  if (const char* e = getenv("ORC_ZINIT")) o.zinit = atoi(e);
+  if (const char* e = getenv("ORC_KEPS")) o.kappa_eps = atof(e);
+  if (const char* e = getenv("ORC_KMU")) o.kappa_mu = atof(e);
+  if (const char* e = getenv("ORC_TMU")) o.theta_mu = atof(e);
+  if (const char* e = getenv("ORC_SOC")) o.max_soc = atoi(e);
+  if (const char* e = getenv("ORC_SINGLE")) o.single_dec = atoi(e);
+  if (const char* e = getenv("ORC_RED")) o.red_iters = atoi(e);
+  if (const char* e = getenv("ORC_RZ")) o.rz_kappa = atof(e);
+  if (const char* e = getenv("ORC_BTHR")) o.boost_thr = atof(e);
+  if (const char* e = getenv("ORC_BFAC")) o.boost_fac = atof(e);
+  if (const char* e = getenv("ORC_BCAP")) o.boost_cap = atof(e);
+  if (const char* e = getenv("ORC_BHOLD")) o.boost_hold = atoi(e);
   Ipm ipm(P, p, o);
+  ipm.trace = g_trace; ipm.trace_cap = g_trace_cap;
   int it = 0;
   double kk = 0;
   int status = ipm.solve(x0, it, kk);
@@ -873,5 +1086,8 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
   *kkt = kk;
   return status;
 }
+
+long orc_soc_count(int which) { return which ? g_soc_accepted.load() : g_soc_solves.load(); }
+void orc_set_trace(double* buf, int cap) { g_trace = buf; g_trace_cap = cap; }
 
 }  // extern "C"
