@@ -237,6 +237,8 @@ struct Config {
   double mu_init, bound_push;
   double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
   double boost_fac, boost_cap;   // re-centring of a crawling iteration (bmpc_ipm.cuh): mu <- min(cap, fac * mu)
+  int max_soc;                   // second-order corrections per iteration (0 or 1)
+  int slice_iters;               // iterations of pass A of the two-pass scheduling (bmpc_ipm.cuh)
   int red_iters;                 // ... when the optimality error has not improved on any of the last red_iters iterates (<= 4)
   double gamma_theta, gamma_phi, eta_phi, s_phi, s_theta;
   // integration coefficients of the piecewise-linear jerk at t = h (App. A.4)

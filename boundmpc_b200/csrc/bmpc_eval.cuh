@@ -74,4 +74,26 @@ BMPC_DEV void eval_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   BMPC_SYNC();
 }
 
+
+// One Newton step of the interior-point iteration at a given primal-dual point (parity tests only: the Riccati sweep
+// against a dense solve of the assembled KKT system).  v [n + 36 N + 12 N + 12 N + n + n] = x, y, s, z_s, z_L,
+// z_U; out: dx [n], ynew [36 N] (the equality multipliers of the full step), ok (0: some Q_uu was not positive definite).
+struct KktIO { const double* v; const double* p; double mu, delta_w; double* dx; double* ynew; int32_t* ok; };
+BMPC_DEV void kkt_step_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const KktIO& io) {
+  const int N = C.N, n = C.n, ne = NE * N, nd = ND * N;
+  build_wp0(cx, C, io.p, W.wp0);
+  const double* q = io.v;
+  PAR_FOR(i, n) { W.x[i] = q[i]; W.zL[i] = q[n + ne + 2 * nd + i]; W.zU[i] = q[2 * n + ne + 2 * nd + i]; }
+  PAR_FOR(i, ne) W.y[i] = q[n + i];
+  PAR_FOR(i, nd) { W.s[i] = q[n + ne + i]; W.zs[i] = q[n + ne + nd + i]; }
+  BMPC_SYNC();
+  eval_full(cx, C, W, io.p, W.x);
+  kkt_prepare(cx, C, W, io.mu);
+  const bool ok = kkt_solve(cx, C, W, io.p, S, io.delta_w);
+  PAR_FOR(i, n) io.dx[i] = W.dx[i];
+  PAR_FOR(i, ne) io.ynew[i] = W.ynew[i];
+  if (cx.tid == 0) *io.ok = ok ? 1 : 0;
+  BMPC_SYNC();
+}
+
 }  // namespace bmpc

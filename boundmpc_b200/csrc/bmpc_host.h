@@ -41,6 +41,10 @@ inline int make_config(const bmpc_config& in, Config& C) {
   // Re-centring (see bmpc_ipm.cuh): Ipopt's kkt-error progress test with adaptive_mu_kkterror_red_iters = 3; a crawling
   // iteration gets mu <- min(1, 10 mu).  Longest solve of the 65,536-instance bench workload 125 -> 55 iterations.
   C.red_iters = 3; C.boost_fac = 10.0; C.boost_cap = 1.0;
+  C.slice_iters = 6;
+  // One second-order correction per iteration (Ipopt: max_soc = 4; on the bench workload a second correction is never
+  // accepted when the first is not): 0.9 % extra KKT solves, 7 % fewer iterations along the experiment1 closed loop.
+  C.max_soc = 1;
   C.gamma_theta = 1e-5; C.gamma_phi = 1e-5; C.eta_phi = 1e-8; C.s_phi = 2.3; C.s_theta = 1.1;
   const double h = in.dt;
   C.a_dq = h; C.a_ddq = h * h / 2; C.a_um = h * h * h / 8; C.a_u = h * h * h / 24;

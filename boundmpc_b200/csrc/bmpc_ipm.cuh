@@ -41,16 +41,73 @@ struct InstanceIO {
 
 BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 
-// Two-pass scheduling of a batch (k_solve): pass A runs the first SLICE_ITERS iterations of every instance and
-// parks the iterate in global memory; pass B resumes the parked instances, those whose optimality error has grown
-// over the slice ("hard": the few instances that go on for 50-150 iterations) first.  Starting the long solves
-// early keeps them out of the tail of the launch (longest-processing-time-first; the work queue alone leaves
-// 30 % of the GPU idle behind them on the bench workload).  Results do not depend on where an instance is parked.
-constexpr int SLICE_ITERS = 6;
+// Two-pass scheduling of a batch (k_solve): pass A runs the first C.slice_iters iterations of every instance and
+// parks the iterate in global memory; pass B resumes the parked instances in the order of the work they have left
+// (longest-processing-time-first): SCHED_LISTS priority lists, list 0 = "hard" (the few instances that go on for 20-50
+// iterations: optimality error grown over the slice, barrier parameter raised, or steps cut to a crawl), the others by
+// the size of the optimality error at the slice boundary, which predicts the remaining iterations to +-2 (bench
+// workload: e0 >= 0.1: 6-8 to go, >= 1e-4: ~4, below: 1-2).  A plain work queue leaves 30 % of the GPU idle behind the
+// long solves; two lists (hard / normal) still 8 % behind the ordinary 15-iteration ones picked up last.  Results do not
+// depend on where an instance is parked.
+constexpr int SCHED_LISTS = 4;
 constexpr int SAVE_FILT = 128, SAVE_SCAL = 16;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4])
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
 enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
-enum { DONE = 0, PARKED = 1, PARKED_HARD = 2 };                  // its return value
+enum { DONE = 0, PARKED = 1 };                                   // its return value: DONE or PARKED + priority list
+
+// Remaining components of the Newton step (slacks, bound and slack multipliers) from dx, with the fraction-to-the-boundary
+// limits of the primal and the dual step, the slope of the barrier objective along the step and the barrier terms of the
+// current point: sv4 = {alpha_pr_max, alpha_du_max, dphi, phi_barrier}.  The inequality residual is read as W.d + W.s
+// (the second-order correction puts its own residual there).
+BMPC_NOINLINE void step_parts(const Ctx cx, const Config& C, const Work& W, double mu, double (&sv4)[4]) {
+  const int n = C.n, nd = ND * C.N;
+  // ---- remaining step components, fraction to the boundary, barrier objective and its slope
+  const double tau = fmax(C.tau_min, 1.0 - mu);
+  sv4[0] = 1.0; sv4[1] = 1.0; sv4[2] = 0.0; sv4[3] = 0.0;   // alpha_pr, alpha_du, dphi, phi_cur(barrier part)
+  PAR_FOR(i, nd) {
+    const int k = i / ND, r = i - ND * k;
+    const double* JD = W.rec + (size_t)k * R_SIZE + R_JD + r * 8;
+    const double* dw = W.dx + NX * k;
+    double jd = JD[6] * dw[oPHI] + JD[7] * dw[oDPHI];
+    for (int q = 0; q < 6; q++) jd += JD[q] * dw[oPPOS + q];
+    const double sv = W.s[i], zv = W.zs[i];
+    const double dsv = -(W.d[i] + sv) - jd, isv = 1.0 / sv;
+    const double dzv = mu * isv - zv - zv * isv * dsv;
+    W.ds[i] = dsv; W.dzs[i] = dzv;
+    if (dsv < 0) sv4[0] = fmin(sv4[0], -tau * sv / dsv);
+    if (dzv < 0) sv4[1] = fmin(sv4[1], -tau * zv / dzv);
+    sv4[2] -= mu * dsv * isv;
+    sv4[3] -= mu * bmpc_log(sv);
+  }
+  PAR_FOR(i, n) {
+    const int a = i % NX;
+    const double l = C.lb[a], u = C.ub[a], dxi = W.dx[i];
+    double dl = 0.0, du = 0.0;
+    sv4[2] += W.gradf[i] * dxi;
+    if (l > -1e300) {
+      const double sl = W.x[i] - l, z = W.zL[i], isl = 1.0 / sl;
+      dl = mu * isl - z - z * isl * dxi;
+      if (dxi < 0) sv4[0] = fmin(sv4[0], -tau * sl / dxi);
+      if (dl < 0) sv4[1] = fmin(sv4[1], -tau * z / dl);
+      sv4[2] -= mu * dxi * isl;
+      sv4[3] -= mu * bmpc_log(sl);
+    }
+    if (u < 1e300) {
+      const double su = u - W.x[i], z = W.zU[i], isu = 1.0 / su;
+      du = mu * isu - z + z * isu * dxi;
+      if (dxi > 0) sv4[0] = fmin(sv4[0], tau * su / dxi);
+      if (du < 0) sv4[1] = fmin(sv4[1], -tau * z / du);
+      sv4[2] += mu * dxi * isu;
+      sv4[3] -= mu * bmpc_log(su);
+    }
+    W.dzL[i] = dl; W.dzU[i] = du;
+  }
+  {
+    const int ops[4] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM};
+    block_reduce<4>(cx, sv4, ops);
+  }
+  BMPC_TMARK(18);
+}
 
 BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& S, const InstanceIO& io, int mode = RUN_FULL,
                             double* save = nullptr) {
@@ -118,7 +175,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   const double nzcnt = (double)N * (ND + nbnd);
 
   for (;; it++) {
-    if (mode == RUN_SLICE && it == SLICE_ITERS) {
+    if (mode == RUN_SLICE && it == C.slice_iters) {
       // ---- park the iterate (every quantity the loop carries; everything else is recomputed by eval_full)
       double* q = save;
       PAR_FOR(i, n) { q[i] = W.x[i]; q[n + i] = W.zL[i]; q[2 * n + i] = W.zU[i]; }
@@ -136,10 +193,10 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         for (int r = 0; r < 4; r++) q[12 + r] = refs[r];
       }
       BMPC_SYNC();
-      // "hard": the optimality error has grown over the slice, the barrier parameter has been raised, or the
-      // fraction-to-the-boundary rule has cut the steps to less than 0.3 on average -- on the bench workload these
-      // tests flag 6 % of the batch and every instance with more than 22 iterations to go
-      return (kkt_final > e0_first || mu_top > C.mu_init || apr_sum < 0.3 * it) ? PARKED_HARD : PARKED;
+      // priority list (see SCHED_LISTS).  "hard": on the bench workload these tests flag 6 % of the batch and every
+      // instance with more than 22 iterations to go
+      if (kkt_final > e0_first || mu_top > C.mu_init || apr_sum < 0.3 * it) return PARKED + 0;
+      return PARKED + (kkt_final >= 0.1 ? 1 : (kkt_final >= 1e-4 ? 2 : 3));
     }
     eval_full(cx, C, W, p, W.x);
     // ---- optimality error (Ipopt's E_mu), constraint violation theta
@@ -278,55 +335,12 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       if (!ok) { status = ST_REGULARIZATION; break; }
       delta_w_last = dwreg;
     }
-    // ---- remaining step components, fraction to the boundary, barrier objective and its slope
-    const double tau = fmax(C.tau_min, 1.0 - mu);
-    double sv4[4] = {1.0, 1.0, 0.0, 0.0};   // alpha_pr, alpha_du, dphi, phi_cur(barrier part)
-    PAR_FOR(i, nd) {
-      const int k = i / ND, r = i - ND * k;
-      const double* JD = W.rec + (size_t)k * R_SIZE + R_JD + r * 8;
-      const double* dw = W.dx + NX * k;
-      double jd = JD[6] * dw[oPHI] + JD[7] * dw[oDPHI];
-      for (int q = 0; q < 6; q++) jd += JD[q] * dw[oPPOS + q];
-      const double sv = W.s[i], zv = W.zs[i];
-      const double dsv = -(W.d[i] + sv) - jd, isv = 1.0 / sv;
-      const double dzv = mu * isv - zv - zv * isv * dsv;
-      W.ds[i] = dsv; W.dzs[i] = dzv;
-      if (dsv < 0) sv4[0] = fmin(sv4[0], -tau * sv / dsv);
-      if (dzv < 0) sv4[1] = fmin(sv4[1], -tau * zv / dzv);
-      sv4[2] -= mu * dsv * isv;
-      sv4[3] -= mu * bmpc_log(sv);
-    }
-    PAR_FOR(i, n) {
-      const int a = i % NX;
-      const double l = C.lb[a], u = C.ub[a], dxi = W.dx[i];
-      double dl = 0.0, du = 0.0;
-      sv4[2] += W.gradf[i] * dxi;
-      if (l > -1e300) {
-        const double sl = W.x[i] - l, z = W.zL[i], isl = 1.0 / sl;
-        dl = mu * isl - z - z * isl * dxi;
-        if (dxi < 0) sv4[0] = fmin(sv4[0], -tau * sl / dxi);
-        if (dl < 0) sv4[1] = fmin(sv4[1], -tau * z / dl);
-        sv4[2] -= mu * dxi * isl;
-        sv4[3] -= mu * bmpc_log(sl);
-      }
-      if (u < 1e300) {
-        const double su = u - W.x[i], z = W.zU[i], isu = 1.0 / su;
-        du = mu * isu - z + z * isu * dxi;
-        if (dxi > 0) sv4[0] = fmin(sv4[0], tau * su / dxi);
-        if (du < 0) sv4[1] = fmin(sv4[1], -tau * z / du);
-        sv4[2] += mu * dxi * isu;
-        sv4[3] -= mu * bmpc_log(su);
-      }
-      W.dzL[i] = dl; W.dzU[i] = du;
-    }
-    {
-      const int ops[4] = {RED_MIN, RED_MIN, RED_SUM, RED_SUM};
-      block_reduce<4>(cx, sv4, ops);
-    }
-    BMPC_TMARK(18);
-    const double apr = sv4[0], adu = sv4[1], dphi = sv4[2], phi_cur = fval + sv4[3];
+    double sv4[4];
+    step_parts(cx, C, W, mu, sv4);
+    const double apr = sv4[0], dphi = sv4[2], phi_cur = fval + sv4[3];
+    double adu = sv4[1];
     apr_sum += apr;
-    // ---- filter line search (Waechter & Biegler 2006, Alg. A, without restoration phase / SOC)
+    // ---- filter line search (Waechter & Biegler 2006, Alg. A) with one second-order correction (Sec. 2.4; Ipopt max_soc)
     double alpha = apr;
     bool accepted = false, ftype = false;
     const int nfilt = S.flag[1];
@@ -335,7 +349,10 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     // iterations while the dual infeasibility stays above tol); Newton's full step is taken instead, as Ipopt does for
     // its "tiny steps"
     const bool flat = th_cur <= 1e-10 && fabs(dphi) <= 1e-10 * fmax(1.0, fabs(phi_cur));
-    for (int ls = 0; ls < 40; ls++, alpha *= 0.5) {
+    // soc: 0 = regular trials, 1 = the trial of the corrected step is being tested (alpha = its fraction-to-the-boundary limit,
+    // acceptance still measured with the length a_sw = apr of the rejected full step), 2 = correction used up
+    int soc = C.max_soc > 0 ? 0 : 2;
+    for (int ls = 0; ls < 40;) {
       PAR_FOR(i, n) W.xt[i] = W.x[i] + alpha * W.dx[i];
       PAR_FOR(i, nd) W.st[i] = W.s[i] + alpha * W.ds[i];
       BMPC_SYNC();
@@ -357,26 +374,74 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       }
       BMPC_TMARK(20);
       const double th_t = tv2[0], ph_t = tv2[1];
-      if (!(th_t == th_t) || !(ph_t == ph_t) || !(th_t < 1e300) || !(fabs(ph_t) < 1e300) || th_t > theta_max) continue;
-      if (flat) { accepted = true; ftype = true; break; }
-      bool filt_ok = true;
-      for (int q = 0; q < nfilt; q++)
-        if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }
-      if (!filt_ok) continue;
-      const bool sw = dphi < 0 && alpha * bmpc_pow(-dphi, C.s_phi) > (th_cur > 0 ? bmpc_pow(th_cur, C.s_theta) : 0.0);
-      // comparisons with Ipopt's round-off allowance (Compare_le: lhs - rhs <= 10 eps |reference value|): close to the
-      // solution the decrease conditions are decided by rounding noise, and a strict test sends the iteration into
-      // dozens of useless backtracking steps (seen on the device: 87 instead of 11 iterations on a bench instance)
-      const double ro = 10 * 2.220446049250313e-16;
-      if (th_cur <= theta_min && sw) {
-        if (ph_t - phi_cur - C.eta_phi * alpha * dphi <= ro * fabs(phi_cur)) { accepted = true; ftype = true; break; }
-      } else {
-        if (th_t - (1 - C.gamma_theta) * th_cur <= ro * fabs(th_cur) ||
-            ph_t - phi_cur + C.gamma_phi * th_cur <= ro * fabs(phi_cur)) { accepted = true; ftype = false; break; }
+      const double a_sw = soc == 1 ? apr : alpha;
+      const bool fin = (th_t == th_t) && (ph_t == ph_t) && (th_t < 1e300) && (fabs(ph_t) < 1e300);
+      bool acc = false, ft = false;
+      if (fin && !(th_t > theta_max)) {
+        if (flat) { acc = true; ft = true; }
+        else {
+          bool filt_ok = true;
+          for (int q = 0; q < nfilt; q++)
+            if (!(th_t < S.filt[2 * q] || ph_t < S.filt[2 * q + 1])) { filt_ok = false; break; }
+          if (filt_ok) {
+            const bool sw = dphi < 0 && a_sw * bmpc_pow(-dphi, C.s_phi) > (th_cur > 0 ? bmpc_pow(th_cur, C.s_theta) : 0.0);
+            // comparisons with Ipopt's round-off allowance (Compare_le: lhs - rhs <= 10 eps |reference value|): close to
+            // the solution the decrease conditions are decided by rounding noise, and a strict test sends the iteration
+            // into dozens of useless backtracking steps (seen on the device: 87 instead of 11 iterations on a bench instance)
+            const double ro = 10 * 2.220446049250313e-16;
+            if (th_cur <= theta_min && sw) {
+              if (ph_t - phi_cur - C.eta_phi * a_sw * dphi <= ro * fabs(phi_cur)) { acc = true; ft = true; }
+            } else {
+              if (th_t - (1 - C.gamma_theta) * th_cur <= ro * fabs(th_cur) ||
+                  ph_t - phi_cur + C.gamma_phi * th_cur <= ro * fabs(phi_cur)) { acc = true; ft = false; }
+            }
+          }
+        }
       }
+      if (acc) { accepted = true; ftype = ft; break; }
+      if (soc == 0 && ls == 0 && fin && th_t >= th_cur) {
+        // ---- second-order correction: the full step has not reduced the constraint violation (the Maratos effect of the
+        // kinematic rows).  Re-solve with the residuals c_soc = alpha c(x_k) + c(x_k + alpha dx) and this iteration's
+        // Hessian perturbation.  W.c / W.d / W.gh are overwritten (the next evaluation rebuilds them); the slack part of g^
+        // changes by sum_r J_d,r Sigma_r (rd_soc,r - rd_r).
+        PAR_FOR(i, ne) W.c[i] = alpha * W.c[i] + W.ct[i];
+        PAR_FOR(i, nd) {
+          const double rd = W.d[i] + W.s[i], rds = alpha * rd + (W.dtr[i] + W.st[i]);
+          W.d[i] = rds - W.s[i];
+          W.st[i] = rds - rd;
+        }
+        BMPC_SYNC();
+        PAR_FOR(it8, 8 * N) {
+          const int k = it8 >> 3, ya = it8 & 7;
+          const double* rec = W.rec + (size_t)k * R_SIZE;
+          double g = 0.0;
+#pragma unroll
+          for (int r = 0; r < ND; r++) g += rec[R_JD + r * 8 + ya] * rec[R_SIG + r] * W.st[ND * k + r];
+          W.gh[NX * k + yrow(ya)] += g;
+        }
+        BMPC_SYNC();
+        soc = 1;
+        if (kkt_solve(cx, C, W, p, S, dwreg)) {
+          step_parts(cx, C, W, mu, sv4);
+          alpha = sv4[0]; adu = sv4[1];
+          continue;                      // test the corrected step (ls stays 0)
+        }
+      }
+      if (soc == 1) {
+        // the corrected step was rejected (or could not be computed): back to the Newton step of this iteration
+        soc = 2;
+        eval_values(cx, C, W, p, W.x, W.c, W.d);
+        kkt_prepare(cx, C, W, mu);
+        kkt_solve(cx, C, W, p, S, dwreg);
+        step_parts(cx, C, W, mu, sv4);
+        adu = sv4[1];
+        alpha = apr;
+      }
+      ls++; alpha *= 0.5;
     }
     if (!accepted) {
-      // no restoration phase: clear the filter and take a strongly damped interior step
+      // no acceptable trial point: clear the filter and take a strongly damped interior step (in place of Ipopt's
+      // restoration phase: 0.1 % of the iterations of the bench workload end here)
       alpha = apr * 0.015625;
       if (++ls_fail > 8) { status = ST_LINESEARCH; break; }
       BMPC_SYNC();

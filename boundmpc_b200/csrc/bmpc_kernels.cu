@@ -55,12 +55,12 @@ extern "C" int bmpc_phase_cycles(unsigned long long* out, int reset) {
 #endif
 
 // Work queue of a launch (first 256 bytes of the workspace).  Single pass (batch <= grid): `next` hands out instances.
-// Two passes (see SLICE_ITERS in bmpc_ipm.cuh): `next` hands out the pass-A slices; a CTA that has parked an instance
-// appends it to the hard or the normal list (tail, then the slot, then `parked`); once pass A is handed out, CTAs pop
-// the hard list first, then the normal list, and leave when every slice has been parked or finished and both lists
-// are drained.
-struct Sched { unsigned int next, sliced, tail_h, head_h, tail_n, head_n; };
-struct SchedMem { Sched* sc; int* list_h; int* list_n; double* save; size_t save_stride; int two_pass; };
+// Two passes (see SCHED_LISTS in bmpc_ipm.cuh): `next` hands out the pass-A slices; a CTA that has parked an instance
+// appends it to its priority list (tail, then the slot, then `sliced`); once pass A is handed out, CTAs pop the lists in
+// priority order and leave when every slice has been parked or finished and all lists are drained.
+struct Sched { unsigned int next, sliced, tail[SCHED_LISTS], head[SCHED_LISTS]; };
+static_assert(sizeof(Sched) <= 256, "queue header");
+struct SchedMem { Sched* sc; int* list; int batch; double* save; size_t save_stride; int two_pass; };   // list [SCHED_LISTS][batch]
 
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
 
@@ -72,10 +72,10 @@ __device__ int sched_next(const SchedMem& M, int batch, int* mode) {
   if (!M.two_pass) return -1;
   *mode = RUN_RESUME;
   for (;;) {
-    for (int which = 0; which < 2; which++) {
-      unsigned int* head = which ? &sc->head_n : &sc->head_h;
-      const unsigned int* tail = which ? &sc->tail_n : &sc->tail_h;
-      const int* list = which ? M.list_n : M.list_h;
+    for (int which = 0; which < SCHED_LISTS; which++) {
+      unsigned int* head = &sc->head[which];
+      const unsigned int* tail = &sc->tail[which];
+      const int* list = M.list + (size_t)which * M.batch;
       for (;;) {
         const unsigned int h = ld_volatile_u32(head);
         if (h >= ld_volatile_u32(tail)) break;
@@ -88,7 +88,9 @@ __device__ int sched_next(const SchedMem& M, int batch, int* mode) {
     }
     if (ld_volatile_u32(&sc->sliced) >= (unsigned int)batch) {
       __threadfence();
-      if (ld_volatile_u32(&sc->head_h) >= ld_volatile_u32(&sc->tail_h) && ld_volatile_u32(&sc->head_n) >= ld_volatile_u32(&sc->tail_n)) return -1;
+      bool empty = true;
+      for (int which = 0; which < SCHED_LISTS; which++) empty = empty && ld_volatile_u32(&sc->head[which]) >= ld_volatile_u32(&sc->tail[which]);
+      if (empty) return -1;
     } else {
       __nanosleep(1000);
     }
@@ -155,15 +157,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
     }
     const int rc = solve_instance(cx, C, W, S, ii, mode, M.save ? M.save + (size_t)b * M.save_stride : nullptr);
 #ifdef BMPC_TRACE
-    if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 3 : 1)] = gtime() | (rc == PARKED_HARD ? 1ull : 0ull);
+    if (threadIdx.x == 0 && b < 65536) g_trace[4 * b + (mode == RUN_RESUME ? 3 : 1)] = gtime() | (rc == PARKED ? 1ull : 0ull);
 #endif
     if (mode == RUN_SLICE) {
       __threadfence();          // the parked iterate, written by all threads, before the list entry that publishes it
       __syncthreads();
       if (threadIdx.x == 0) {
         if (rc != DONE) {
-          const unsigned int slot = atomicAdd(rc == PARKED_HARD ? &M.sc->tail_h : &M.sc->tail_n, 1u);
-          *(volatile int*)((rc == PARKED_HARD ? M.list_h : M.list_n) + slot) = b;
+          const int which = rc - PARKED;
+          const unsigned int slot = atomicAdd(&M.sc->tail[which], 1u);
+          *(volatile int*)(M.list + (size_t)which * M.batch + slot) = b;
           __threadfence();
         }
         atomicAdd(&M.sc->sliced, 1u);
@@ -331,6 +334,30 @@ __global__ void __launch_bounds__(PREP_THREADS) k_finish(const __grid_constant__
   }
 }
 
+// k_kkt: one Newton step per instance at caller-supplied primal-dual points (parity tests, bmpc_eval.cuh)
+struct KktBatchIO { const double* v; const double* p; const double* mu; const double* dw; double* dx; double* ynew; int32_t* ok; };
+__global__ void __launch_bounds__(BMPC_MAX_THREADS) k_kkt(const __grid_constant__ Config C, int batch, KktBatchIO io, double* ws,
+                                                          size_t ws_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+#ifdef BMPC_TIMING
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red, S.tm};
+#else
+  Ctx cx{(int)threadIdx.x, (int)blockDim.x, S.red};
+#endif
+  Work W;
+  work_carve(W, ws + (size_t)blockIdx.x * ws_stride, C.N);
+  work_attach_smem(W, S, C.N);
+  build_tables(cx, C, S);
+  phase_kin_jacobian_init(cx, C, W);
+  const size_t n = C.n, ne = (size_t)NE * C.N, nv = 3 * n + ne + 2 * (size_t)ND * C.N;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    KktIO k{io.v + b * nv, io.p + (size_t)b * C.np, io.mu[b], io.dw[b], io.dx + b * n, io.ynew + b * ne, io.ok + b};
+    kkt_step_instance(cx, C, W, S, k);
+    __syncthreads();
+  }
+}
+
 // FP64 pipe peak probes (roofline denominator).  Each thread runs 8 independent
 // dependency chains so the DFMA / DMMA pipe is the only limiter.
 __global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters) {
@@ -383,6 +410,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 struct bmpc_handle {
   Config C;
   int device, threads, sms, ctas_per_sm, variant;
+  int single_pass, no_zero_copy;   // development switches, read from the environment once in bmpc_create
   int variant_lat;     // launch shape for batches of at most one instance per SM (-1: none): more threads per instance
   size_t ws_stride;    // doubles per CTA slot
   int64_t launches;
@@ -458,6 +486,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   if (h->variant_lat >= 0) e = cudaFuncSetAttribute(kVariants[h->variant_lat].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kVariants[h->variant].fn, h->threads, sizeof(Smem));
@@ -465,6 +494,9 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->ctas_per_sm = want_c < occ ? want_c : occ;
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
   h->launches = 0;
+  h->single_pass = getenv("BMPC_SINGLE_PASS") != nullptr;
+  h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
+  if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
   h->dbuf = nullptr; h->dbuf_bytes = 0;
   h->pin = nullptr; h->pin_bytes = 0;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -500,7 +532,7 @@ int bmpc_workspace_bytes(const bmpc_handle* h, int32_t batch, size_t* bytes) {
   if (!h || !bytes || batch < 0) return fail(BMPC_E_INVALID, "bmpc_workspace_bytes: invalid argument");
   const int b = batch > 0 ? batch : 1, grid = grid_for(h, b);
   *bytes = 256 + (size_t)grid * h->ws_stride * sizeof(double);
-  if (b > grid) *bytes += align_up((size_t)2 * b * sizeof(int), 256) + (size_t)b * align_up(save_doubles(h->C.N), 32) * sizeof(double);   // two-pass scheduling
+  if (b > grid) *bytes += align_up((size_t)SCHED_LISTS * b * sizeof(int), 256) + (size_t)b * align_up(save_doubles(h->C.N), 32) * sizeof(double);   // two-pass scheduling
   return BMPC_OK;
 }
 
@@ -564,16 +596,15 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
   // workspace: [queue 256 B][per-CTA slices][parked lists 2 x batch int][parked iterates batch x save_stride]
   char* wsb = (char*)workspace;
   double* ws = (double*)(wsb + 256);
-  SchedMem M{(Sched*)wsb, nullptr, nullptr, nullptr, 0, 0};
+  SchedMem M{(Sched*)wsb, nullptr, batch, nullptr, 0, 0};
   CU(cudaMemsetAsync(wsb, 0, 256, st));
-  if (batch > grid && !getenv("BMPC_SINGLE_PASS")) {
-    const size_t o_list = 256 + (size_t)grid * h->ws_stride * sizeof(double), list_bytes = align_up((size_t)2 * batch * sizeof(int), 256);
-    M.list_h = (int*)(wsb + o_list);
-    M.list_n = M.list_h + batch;
+  if (batch > grid && !h->single_pass) {
+    const size_t o_list = 256 + (size_t)grid * h->ws_stride * sizeof(double), list_bytes = align_up((size_t)SCHED_LISTS * batch * sizeof(int), 256);
+    M.list = (int*)(wsb + o_list);
     M.save = (double*)(wsb + o_list + list_bytes);
     M.save_stride = align_up(save_doubles(h->C.N), 32);
     M.two_pass = 1;
-    CU(cudaMemsetAsync(M.list_h, 0xFF, (size_t)2 * batch * sizeof(int), st));
+    CU(cudaMemsetAsync(M.list, 0xFF, (size_t)SCHED_LISTS * batch * sizeof(int), st));
   }
   BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status, x0_src, p_src};
   const int v = (h->variant_lat >= 0 && batch <= h->sms) ? h->variant_lat : h->variant;
@@ -600,7 +631,7 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   // Small batches in pageable memory (the single MPC step of a Python / ROS caller): ten small copies around the launch
   // cost more than the transfers themselves.  They are staged through a page-locked area of the handle, which the
   // kernel reads and writes itself (see below): two host memcpys and one launch.
-  if (batch <= BMPC_STAGE_MAX && !getenv("BMPC_NO_ZERO_COPY") && !(is_mapped_host(x0) && is_mapped_host(x))) {
+  if (batch <= BMPC_STAGE_MAX && !h->no_zero_copy && !(is_mapped_host(x0) && is_mapped_host(x))) {
     const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
@@ -643,7 +674,7 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   // the CTA that starts an instance fetches its x0 / p (7.5 KB) into the device buffers, which it then reads throughout
   // the solve; pageable inputs are copied before the launch.
   auto mapped = [&](const void* host) -> void* {
-    if (!host || getenv("BMPC_NO_ZERO_COPY")) return nullptr;
+    if (!host || h->no_zero_copy) return nullptr;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
@@ -836,7 +867,7 @@ int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const d
   if (lam) CU(cudaMemcpyAsync(d + o_l, lam, B * nl * 8, cudaMemcpyHostToDevice, st));
   EvalBatchIO io{(double*)(d + o_x), (double*)(d + o_p), lam ? (double*)(d + o_l) : nullptr, (double*)(d + o_f), (double*)(d + o_g),
                  (double*)(d + o_d), (double*)(d + o_gr), jac ? (double*)(d + o_j) : nullptr, hess ? (double*)(d + o_h) : nullptr};
-  k_eval<<<grid, h->threads, sizeof(Smem), st>>>(h->C, batch, io, (double*)(d + o_ws), h->ws_stride);
+  k_eval<<<grid, h->threads < BMPC_MAX_THREADS ? h->threads : BMPC_MAX_THREADS, sizeof(Smem), st>>>(h->C, batch, io, (double*)(d + o_ws), h->ws_stride);
   CU(cudaGetLastError());
   h->launches += 1;
   if (f) CU(cudaMemcpyAsync(f, d + o_f, B * 8, cudaMemcpyDeviceToHost, st));
@@ -845,6 +876,39 @@ int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const d
   if (grad) CU(cudaMemcpyAsync(grad, d + o_gr, B * n * 8, cudaMemcpyDeviceToHost, st));
   if (jac) CU(cudaMemcpyAsync(jac, d + o_j, B * nl * n * 8, cudaMemcpyDeviceToHost, st));
   if (hess) CU(cudaMemcpyAsync(hess, d + o_h, B * n * n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return BMPC_OK;
+}
+
+int bmpc_kkt_step_batch_host(bmpc_handle* h, int32_t batch, const double* v, const double* p, const double* mu, const double* delta_w,
+                             double* dx, double* ynew, int32_t* ok) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_kkt_step_batch_host: null handle");
+  if (batch < 0 || !v || !p || !mu || !delta_w || !dx || !ynew || !ok) return fail(BMPC_E_INVALID, "bmpc_kkt_step_batch_host: null buffer");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, ne = (size_t)NE * h->C.N, nv = 3 * n + ne + 2 * (size_t)ND * h->C.N, np = h->C.np;
+  const int grid = grid_for(h, batch);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_v = take(B * nv * 8), o_p = take(B * np * 8), o_mu = take(B * 8), o_dw = take(B * 8), o_dx = take(B * n * 8),
+               o_y = take(B * ne * 8), o_ok = take(B * 4), o_ws = take((size_t)grid * h->ws_stride * 8);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(d + o_v, v, B * nv * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_p, p, B * np * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_mu, mu, B * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_dw, delta_w, B * 8, cudaMemcpyHostToDevice, st));
+  KktBatchIO io{(double*)(d + o_v), (double*)(d + o_p), (double*)(d + o_mu), (double*)(d + o_dw), (double*)(d + o_dx), (double*)(d + o_y),
+                (int32_t*)(d + o_ok)};
+  const int thr = h->threads < BMPC_MAX_THREADS ? h->threads : BMPC_MAX_THREADS;
+  k_kkt<<<grid, thr, sizeof(Smem), st>>>(h->C, batch, io, (double*)(d + o_ws), h->ws_stride);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaMemcpyAsync(dx, d + o_dx, B * n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ynew, d + o_y, B * ne * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ok, d + o_ok, B * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return BMPC_OK;
 }

@@ -315,6 +315,21 @@ class BatchSolver:
                     "bmpc_eval_batch_host")
         return {"f": f, "g": g, "d": d, "grad": grad, "jac": jac, "hess": hess}
 
+    def kkt_step_batch(self, x, y, s, zs, zL, zU, p, mu, delta_w=0.0):
+        """One Newton step of the interior-point iteration at given primal-dual points (parity tests of the Riccati
+        sweep against a dense KKT solve).  Returns dx [B, n], ynew [B, 36 N], ok [B]."""
+        p = np.ascontiguousarray(np.atleast_2d(p), np.float64)
+        v = np.ascontiguousarray(np.concatenate([np.atleast_2d(a) for a in (x, y, s, zs, zL, zU)], axis=1), np.float64)
+        B = v.shape[0]
+        assert v.shape[1] == 3 * self.n + 60 * self.N and p.shape == (B, self.np)
+        mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, np.float64), (B,)))
+        dw = np.ascontiguousarray(np.broadcast_to(np.asarray(delta_w, np.float64), (B,)))
+        dx, ynew, ok = np.empty((B, self.n)), np.empty((B, 36 * self.N)), np.empty(B, np.int32)
+        P = _cabi.ptr
+        _cabi.check(self._lib.bmpc_kkt_step_batch_host(self._h, B, P(v), P(p), P(mu), P(dw), P(dx), P(ynew), P(ok)),
+                    "bmpc_kkt_step_batch_host")
+        return {"dx": dx, "ynew": ynew, "ok": ok}
+
 
 def setup_optimization_problem(N, nr_joints, nr_segs, dt, u_min, u_max, ut_min, ut_max, q_lim_lower, q_lim_upper,
                                dq_lim_lower, dq_lim_upper, solver_opts):

@@ -180,6 +180,16 @@ int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_table
 int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const double* p, const double* lam,
                          double* f, double* g, double* d, double* grad, double* jac, double* hess);
 
+/* One Newton step of the interior-point iteration at caller-supplied primal-dual points, for parity tests of the
+ * structure-exploiting KKT solve (what MUMPS does for Ipopt: the factorisation of the augmented system)
+ * against a dense solve of the assembled system.  HOST pointers, small batches.
+ *   v      [batch, 3 n + 60 N]: x (n), y (36 N), s (12 N), z_s (12 N), z_L (n), z_U (n)   (interval form, see bmpc_eval_batch_host)
+ *   mu, delta_w [batch]         barrier parameter and Hessian perturbation (inertia correction)
+ *   dx     [batch, n]           primal step;   ynew [batch, 36 N]  equality multipliers of the full step
+ *   ok     [batch]              0: the reduced Hessian is not positive definite for this delta_w (no step returned) */
+int bmpc_kkt_step_batch_host(bmpc_handle* h, int32_t batch, const double* v, const double* p, const double* mu,
+                             const double* delta_w, double* dx, double* ynew, int32_t* ok);
+
 /* name and duration of the kernels launched by the last solve on this handle (diagnostics):
  * number of kernel launches issued by this library since the handle was created */
 int64_t bmpc_launch_count(const bmpc_handle* h);

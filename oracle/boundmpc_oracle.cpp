@@ -308,7 +308,7 @@ struct Opts {
                               // experiments: 1 adaptive with the LOQO oracle, 2 adaptive with a quality-function oracle
   int zinit = 0;              // 0: z = mu_init / slack, 1: z = mu_init (Ipopt warm_start_mult_bound_push)
   double mu_min = 1e-11, mu_max_fact = 1e3;
-  double rz_kappa = 0; int red_iters = 3; int single_dec = 1; int max_soc = 0;
+  double rz_kappa = 0; int red_iters = 3; int single_dec = 1; int max_soc = 1;
   double boost_thr = 0, boost_fac = 10, boost_cap = 1.0; int boost_hold = 0;
 };
 

@@ -58,7 +58,7 @@ int emu_solve_sliced(const bmpc_config* cfg, int batch, const double* x0, const 
   };
   for (int b = 0; b < batch; b++) {
     const int rc = solve_instance(cx, C, W, *S, make_io(b), RUN_SLICE, save.data() + stride * b);
-    hard[b] = rc == DONE ? -1 : (rc == PARKED_HARD ? 1 : 0);
+    hard[b] = rc == DONE ? -1 : (rc == PARKED ? 1 : 0);   // (priority list 0 = "hard")
   }
   for (int b = batch - 1; b >= 0; b--)
     if (hard[b] >= 0) solve_instance(cx, C, W, *S, make_io(b), RUN_RESUME, save.data() + stride * b);
@@ -165,6 +165,26 @@ int emu_eval(const bmpc_config* cfg, int batch, const double* x, const double* p
               d ? d + (size_t)b * ND * C.N : nullptr, grad ? grad + b * n : nullptr, jac ? jac + b * nl * n : nullptr,
               hess ? hess + b * n * n : nullptr};
     eval_instance(cx, C, W, *S, io);
+  }
+  delete S;
+  return 0;
+}
+int emu_kkt_step(const bmpc_config* cfg, int batch, const double* v, const double* p, const double* mu, const double* dw, double* dx,
+                 double* ynew, int32_t* ok) {
+  Config C;
+  if (make_config(*cfg, C)) return -1;
+  std::vector<double> ws(work_doubles(C.N));
+  Smem* S = new Smem;
+  Work W;
+  work_carve(W, ws.data(), C.N);
+  work_attach_smem(W, *S, C.N);
+  Ctx cx{0, 1, S->red};
+  build_tables(cx, C, *S);
+  phase_kin_jacobian_init(cx, C, W);
+  const size_t n = C.n, ne = (size_t)NE * C.N, nv = 3 * n + ne + 2 * (size_t)ND * C.N;
+  for (int b = 0; b < batch; b++) {
+    KktIO io{v + b * nv, p + (size_t)b * C.np, mu[b], dw[b], dx + b * n, ynew + b * ne, ok + b};
+    kkt_step_instance(cx, C, W, *S, io);
   }
   delete S;
   return 0;

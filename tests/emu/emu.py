@@ -167,3 +167,17 @@ def update(tabs, phimax, new_path, cart, state, sector, path_id):
                           sec.ctypes.data_as(i32p), pid.ctypes.data_as(i32p))
     assert rc == 0
     return state, sec, pid
+
+
+def kkt_step(x, y, s, zs, zL, zU, p, mu, delta_w=0.0, N=10, S=4, dt=0.1):
+    """Host build of the kernel's Newton step (Riccati sweep) at given primal-dual points."""
+    p = np.ascontiguousarray(np.atleast_2d(p), float)
+    v = np.ascontiguousarray(np.concatenate([np.atleast_2d(a) for a in (x, y, s, zs, zL, zU)], axis=1), float)
+    B = v.shape[0]
+    mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, float), (B,)))
+    dw = np.ascontiguousarray(np.broadcast_to(np.asarray(delta_w, float), (B,)))
+    dx, ynew, ok = np.empty((B, 44 * N)), np.empty((B, 36 * N)), np.empty(B, np.int32)
+    cfg = make_cfg(N, S, dt)
+    rc = lib().emu_kkt_step(ctypes.byref(cfg), B, _p(v), _p(p), _p(mu), _p(dw), _p(dx), _p(ynew), ok.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert rc == 0
+    return dict(dx=dx, ynew=ynew, ok=ok)
