@@ -27,7 +27,7 @@ class BmpcConfig(ctypes.Structure):
 
 
 EXPORTS = ["bmpc_create", "bmpc_destroy", "bmpc_dims", "bmpc_bounds", "bmpc_workspace_bytes", "bmpc_solve_batch",
-           "bmpc_solve_batch_host", "bmpc_prepare_batch", "bmpc_prepare_batch_host", "bmpc_post_batch", "bmpc_post_batch_host", "bmpc_post_log_batch", "bmpc_update_batch", "bmpc_finish_batch", "bmpc_eval_batch_host", "bmpc_kkt_step_batch_host", "bmpc_launch_count", "bmpc_launch_shape", "bmpc_fp64_peak", "bmpc_last_error"]
+           "bmpc_solve_batch_host", "bmpc_prepare_batch", "bmpc_prepare_batch_host", "bmpc_post_batch", "bmpc_post_batch_host", "bmpc_post_log_batch", "bmpc_update_batch", "bmpc_finish_batch", "bmpc_mpc_step_batch_host", "bmpc_eval_batch_host", "bmpc_kkt_step_batch_host", "bmpc_launch_count", "bmpc_launch_shape", "bmpc_fp64_peak", "bmpc_last_error"]
 
 
 class BmpcError(RuntimeError):
@@ -62,6 +62,7 @@ def lib():
     L.bmpc_post_log_batch.argtypes = [vp, i32, vp, i32, i32] + [vp] * 11
     L.bmpc_update_batch.argtypes = [vp, i32, vp, i32, i32] + [vp] * 7
     L.bmpc_finish_batch.argtypes = [vp, i32, vp, i32, i32] + [vp] * 10 + [i32, vp]
+    L.bmpc_mpc_step_batch_host.argtypes = [vp, i32, vp, i32, i32] + [vp] * 12
     L.bmpc_launch_count.argtypes = [vp]
     L.bmpc_launch_count.restype = ctypes.c_int64
     L.bmpc_launch_shape.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p, c_int32_p]

@@ -9,10 +9,20 @@ host-side `prepare()`.  As in the reference, the cold start (BoundMPC.py:316-321
 drawn from step 0 only (its all-zero path parameter is meaningless further along the path); all
 others use the shifted previous solution (BoundMPC.py:373-375).
 Generated batches are cached as .npz (inputs are never part of a timed region).
+
+Two generators.  The default ("repaired") one is the bench workload: sensor-noise sized perturbations (sigma_q 5e-3),
+bound widths x U(1, 1.25), and a perturbation that puts the start further outside the error bounds than the nominal
+closed loop ever is gets halved (up to five times) -- 99.9 % of its instances are solvable.  `spec=True` is SURVEY 8d
+taken literally: sigma_q = 0.02 rad, sigma_dq = 0.02, sigma_ddq = 0.05, every odd instance cold-started, bound widths
+x U(0.75, 1.25), nothing repaired; a 0.02 rad joint perturbation moves the tool by centimetres while the tight segments
+allow millimetres, so a large share of those instances starts outside its bounds with no feasible way back within the
+jerk limit (they end as "locally infeasible" or fall back on the previous solution in the closed loop).  bench.py
+reports both side by side.
 """
 import copy
 import hashlib
 import os
+import time
 import numpy as np
 
 from . import scenarios
@@ -52,10 +62,12 @@ def _restore(mpc, snap):
     mpc.solver = solver
 
 
-def nominal_sequence(scn, solver, max_steps=600, record=None):
+def nominal_sequence(scn, solver, max_steps=600, record=None, device_step=True, real_time=True):
     """Headless closed loop of one scenario.  Returns the list of per-step
-    (controller snapshot, robot state) pairs and per-step solver statistics."""
-    mpc = make_mpc(scn, solver)
+    (controller snapshot, robot state) pairs and per-step statistics (iterations, time inside the solver call, success,
+    wall time of the whole `BoundMPC.step`).  device_step=False: the numpy mirror around solver(x0=, p=)."""
+    mpc = make_mpc(scn, solver, real_time)
+    mpc.device_step = device_step
     rm = RobotModel()
     q, dq, ddq, jerk, v = scn['q0'].copy(), np.zeros(7), np.zeros(7), np.zeros(7), np.zeros(6)
     x_phi_d = np.array([mpc.phi_max[0], 0.0, 0.0])
@@ -63,10 +75,12 @@ def nominal_sequence(scn, solver, max_steps=600, record=None):
     for step in range(max_steps):
         p_lie = rm.fk(q)
         snaps.append((_snapshot(mpc), dict(q=q.copy(), dq=dq.copy(), ddq=ddq.copy(), jerk=jerk.copy(), v=v.copy())))
+        t_w = time.perf_counter()
         traj, _, _, t_solve, iters = mpc.step(q, dq, ddq, p_lie, v, x_phi_d, jerk)
+        t_w = time.perf_counter() - t_w
         if traj is None:
             raise RuntimeError("nominal sequence: the controller gave up")
-        stats.append((iters, t_solve, mpc.solver.stats()['success']))
+        stats.append((iters, t_solve, mpc.solver.stats()['success'], t_w))
         if record is not None:
             record.append(traj)
         jm = np.concatenate((jerk[:, None], traj['dddq'][:, :2]), axis=1)
@@ -83,30 +97,34 @@ def nominal_sequence(scn, solver, max_steps=600, record=None):
 # start can make the NLP infeasible; `make_batch` halves the perturbation of such an instance
 # until its zero-jerk roll-out is no further outside the bounds than the unperturbed one.
 SIGMA_Q, SIGMA_DQ, SIGMA_DDQ = 5e-3, 2e-2, 5e-2
+SPEC_SIGMA = (2e-2, 2e-2, 5e-2)          # q, dq, ddq
 SCALES = (1.0, 0.5, 0.25, 0.125, 0.0625, 0.0)
 CHECK_STAGES = 3
 
 
-def perturbed_instance(mpc, snaps, x_phi_d, i, bound_scale=False, scale=1.0):
+def perturbed_instance(mpc, snaps, x_phi_d, i, bound_scale=False, scale=1.0, spec=False):
     """Instance i of a batch with the perturbation multiplied by `scale`.
     Returns the warm start, the parameter vector and the zero-jerk roll-out used as
-    feasibility probe."""
+    feasibility probe.  spec: the literal SURVEY 8d generator (module docstring)."""
     rng = np.random.default_rng(SEED0 + i)
     snap, st = snaps[i % len(snaps)]
     _restore(mpc, snap)
-    nq, ndq, nddq = rng.normal(0.0, SIGMA_Q, 7), rng.normal(0.0, SIGMA_DQ, 7), rng.normal(0.0, SIGMA_DDQ, 7)
+    sq, sdq, sddq = SPEC_SIGMA if spec else (SIGMA_Q, SIGMA_DQ, SIGMA_DDQ)
+    nq, ndq, nddq = rng.normal(0.0, sq, 7), rng.normal(0.0, sdq, 7), rng.normal(0.0, sddq, 7)
     q = np.clip(st['q'] + scale * nq, Q_LIM_LOWER + 0.05, Q_LIM_UPPER - 0.05)
     dq = np.clip(st['dq'] + scale * ndq, DQ_LIM_LOWER + 0.05, DQ_LIM_UPPER - 0.05)
     ddq = st['ddq'] + scale * nddq
     if bound_scale:
-        # widths x U(1, 1.25): enlarging e_min / e_max enlarges the quartic bound everywhere, so
-        # the nominal closed-loop state stays feasible (shrinking them would not)
-        f = rng.uniform(1.0, 1.25, 4)
+        # repaired generator: widths x U(1, 1.25) -- enlarging e_min / e_max enlarges the quartic bound everywhere, so
+        # the nominal closed-loop state stays feasible (shrinking them would not); spec: x U(0.75, 1.25)
+        f = rng.uniform(0.75 if spec else 1.0, 1.25, 4)
         rp = mpc.ref_path
         rp.e_p_min = [v * f[0] for v in rp.e_p_min]
         rp.e_p_max = [v * f[1] for v in rp.e_p_max]
         rp.e_r_min = [v * f[2] for v in rp.e_r_min]
         rp.e_r_max = [v * f[3] for v in rp.e_r_max]
+    if spec and i % 2 == 1:
+        mpc.prev_solution = None         # odd instances: cold start (BoundMPC.py:316-321)
     rm = mpc.robot_model
     p0 = rm.fk(q)
     v0 = rm.jacobian_fk(q) @ dq
@@ -224,21 +242,24 @@ class _BoundsOnly:
 _GEN = {}
 
 
-def _gen_init(seqs, bounds, bound_scale):
+def _gen_init(seqs, bounds, bound_scale, spec=False):
     _GEN['b'] = bound_scale
+    _GEN['spec'] = spec
     _GEN['seqs'] = {name: (make_mpc(scn, _BoundsOnly(bounds)), snaps, xd) for name, (scn, snaps, xd) in seqs.items()}
 
 
 def _gen_one(job):
     i, name, scale = job
     mpc, snaps, xd = _GEN['seqs'][name]
-    return perturbed_instance(mpc, snaps, xd, i, _GEN['b'], scale)
+    return perturbed_instance(mpc, snaps, xd, i, _GEN['b'], scale, _GEN['spec'])
 
 
 def make_batch(solver, scenario_names, first, count, n=10, tight=False, bound_scale=False, cache=True, workers=None,
-               return_scales=False):
-    """Instances `first .. first+count-1`; instance i uses scenario_names[i % len(scenario_names)]."""
-    key = f"v6|{scenario_names}|{first}|{count}|{n}|{tight}|{bound_scale}|{SIGMA_Q}|{SIGMA_DQ}|{SIGMA_DDQ}"
+               return_scales=False, spec=False):
+    """Instances `first .. first+count-1`; instance i uses scenario_names[i % len(scenario_names)].
+    `solver` runs the nominal closed loops (any object with the solver call surface) and, for the repaired generator,
+    evaluates the bound excess of the candidates (`eval_batch`)."""
+    key = f"v7|{scenario_names}|{first}|{count}|{n}|{tight}|{bound_scale}|{SIGMA_Q}|{SIGMA_DQ}|{SIGMA_DDQ}|{spec}"
     path = _cache_path(key)
     if cache and os.path.exists(path):
         z = np.load(path)
@@ -259,10 +280,10 @@ def make_batch(solver, scenario_names, first, count, n=10, tight=False, bound_sc
     pool = None
     if workers > 1 and count >= 64:
         import multiprocessing as mp
-        pool = mp.get_context("fork").Pool(workers, initializer=_gen_init, initargs=(seqs, bounds, bound_scale))
+        pool = mp.get_context("fork").Pool(workers, initializer=_gen_init, initargs=(seqs, bounds, bound_scale, spec))
         run = lambda jobs: pool.map(_gen_one, jobs, chunksize=max(1, len(jobs) // (workers * 8)))
     else:
-        _gen_init(seqs, bounds, bound_scale)
+        _gen_init(seqs, bounds, bound_scale, spec)
         run = lambda jobs: [_gen_one(j) for j in jobs]
     try:
         def excess(jobs):
@@ -270,10 +291,17 @@ def make_batch(solver, scenario_names, first, count, n=10, tight=False, bound_sc
             xr = np.stack([r[2] for r in res])
             pp = np.stack([r[1] for r in res])
             return res, bound_excess(solver.eval_batch(xr, pp, want_jac=False, want_hess=False)["d"], n)
+        if spec:                      # literal generator: one pass, nothing repaired
+            res = run([(int(i), nm, 1.0) for i, nm in zip(ids, names)])
+            for j, r in enumerate(res):
+                x0[j], p[j], used[j] = r[0], r[1], 1.0
+            pending_done = True
+        else:
+            pending_done = False
         # unperturbed instances: the level of bound excess the closed loop itself lives with
-        _, ex0 = excess([(int(i), nm, 0.0) for i, nm in zip(ids, names)])
+        _, ex0 = excess([(int(i), nm, 0.0) for i, nm in zip(ids, names)]) if not pending_done else (None, np.zeros(count))
         limit = np.maximum(ex0, -0.02)
-        pending = np.arange(count)
+        pending = np.arange(count) if not pending_done else np.arange(0)
         for scale in SCALES:
             if len(pending) == 0:
                 break
@@ -298,4 +326,5 @@ CONFIGS = {
     "exp2_8192": dict(scenario_names=("exp2",), count=8192, n=10),
     "exp1_N20_tight_8192": dict(scenario_names=("exp1",), count=8192, n=20, tight=True),
     "mixed_65536": dict(scenario_names=("exp1", "exp2"), count=65536, n=10, bound_scale=True),
+    "spec_mixed_65536": dict(scenario_names=("exp1", "exp2"), count=65536, n=10, bound_scale=True, spec=True),
 }

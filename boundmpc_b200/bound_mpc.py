@@ -137,6 +137,9 @@ class BoundMPC:
                 self.solver.generate_dependencies('gen_traj_opt_nlp_deps.cpp', {'cpp': True})
         self._lbg = np.array(self.lbg)
         self._ubg = np.array(self.ubg)
+        self.device_step = True          # step() on the device when the solver offers it (see step)
+        self._tab = self._tab_for = None
+        self._zero_id = np.zeros(1, np.int32)
 
     # ------------------------------------------------------------------ replanning (BoundMPC.py:163-217)
     def update(self, pos_points, rot_points, pos_lim, rot_lim, bp1, br1, s, e_p_min, e_r_min, e_p_max, e_r_max,
@@ -309,7 +312,69 @@ class BoundMPC:
         return None, None, None, None, None
 
     def step(self, q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current, x_des=None):
-        """One MPC step (BoundMPC.py:306-506)."""
+        """One MPC step (BoundMPC.py:306-506).  With the CUDA solver behind it the whole step -- parameter builder, solve,
+        accept / fallback, post-processing and logging branch -- is one library call on the device (`_step_device`);
+        `device_step = False` (or a solver without that entry) takes the numpy mirror around `solver(x0=, p=)`."""
+        if self.device_step and hasattr(self.solver, "mpc_step_host"):
+            return self._step_device(q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current)
+        return self.step_mirror(q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current)
+
+    REF_COLS = (("p", 0, 6), ("dp", 6, 12), ("ddp", 12, 18), ("dp_normed", 18, 21), ("r_par_bound", 21, 22), ("bound_lower", 22, 26),
+                ("bound_upper", 26, 30), ("e_p_off", 30, 32), ("e_r_off", 32, 34), ("bp1", 34, 37), ("bp2", 37, 40), ("br1", 40, 43),
+                ("br2", 43, 46), ("v1", 46, 49), ("v2", 49, 52), ("v3", 52, 55))
+    ERR_KEYS = ("e_p", "de_p", "e_p_par", "e_p_orth", "de_p_par", "de_p_orth", "e_r", "de_r", "e_r_par", "e_r_orth1", "e_r_orth2")
+
+    def _step_device(self, q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current):
+        """`step` through `bmpc_mpc_step_batch_host` (B = 1): this object only packs its state (76 doubles + the previous
+        solution) and unpacks the results into the reference's dictionaries."""
+        N = self.N
+        self.ref_path.update(self.phi_current)       # window slide of get_parameters (the builder kernel then finds nothing to slide)
+        st, sector, prev = self.builder_state(np.asarray(q0, float), np.asarray(dq0, float), np.asarray(ddq0, float),
+                                              np.asarray(p0, float), np.asarray(v0, float), np.asarray(x_phi_d, float),
+                                              np.asarray(jerk_current, float))
+        if self._tab_for is not self.ref_path:
+            self._tab, self._tab_for = np.ascontiguousarray(self.ref_path.path_table()[None]), self.ref_path
+        ec_in = self.error_count
+        t0 = time.perf_counter()
+        r = self.solver.mpc_step_host(self._tab, self._zero_id, [sector], st[None], prev[None], [ec_in], self.log)
+        time_elapsed = time.perf_counter() - t0
+        status, iters, ec = int(r["status"][0]), int(r["iters"][0]), int(r["error_count"][0])
+        self.solver.set_stats(iters, status)
+        so = r["state"][0]
+        accepted = ec == 0
+        assert int(r["sector"][0]) == self.ref_path.sector
+        self.error_count = ec
+        if so[73] != 0.0:
+            self.prev_solution = r["prev"][0]
+        if accepted:
+            self.prev_infeasible_solution = r["x"][0]
+        else:
+            print(f"[ERROR] Could not find feasible solution. Using previous solution. Error count: {ec}")
+            self.prev_infeasible_solution = r["x"][0]
+        if ec >= N:
+            return None, None, None, None, None
+        self.phi_prev = np.copy(self.phi_current)
+        self.phi_current, self.dphi_current = np.array([so[40]]), np.array([so[41]])
+        self.ddphi_current, self.dddphi_current = np.array([so[42]]), np.array([so[43]])
+        self.pr_ref, self.iw_ref = so[44:47].copy(), so[47:50].copy()
+        M = N - ec
+        T = r["traj"][0][:M]
+        W = (r["x"][0] if accepted else prev).reshape(N, -1)
+        traj_data = dict(p=T[:, 0:6].T.copy(), v=T[:, 6:12].T.copy(), a=T[:, 12:18].T.copy(), q=T[:, 18:25].T.copy(),
+                         dq=T[:, 25:32].T.copy(), ddq=T[:, 32:39].T.copy(), dddq=W[ec:, :7].T.copy(), phi=T[:, 39].copy(),
+                         dphi=T[:, 40].copy(), ddphi=T[:, 41].copy(), dddphi=W[ec:, 7].copy())
+        ref_data = err_data = None
+        if self.log:
+            R, E = r["ref"][0][:M], r["err"][0][:M]
+            ref_data, err_data = defaultdict(list), defaultdict(list)
+            for key, a, b in self.REF_COLS:
+                ref_data[key] = [R[i, a:b].copy() for i in range(M)]
+            for k_, key in enumerate(self.ERR_KEYS):
+                err_data[key] = [E[i, 3 * k_:3 * k_ + 3].copy() for i in range(M)]
+        return traj_data, ref_data, err_data, time_elapsed, iters
+
+    def step_mirror(self, q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current, x_des=None):
+        """One MPC step with the numpy mirror of the reference's pre- / post-processing around `solver(x0=, p=)`."""
         w0, params, aux = self.prepare(q0, dq0, ddq0, p0, v0, x_phi_d, jerk_current)
         t0 = time.perf_counter()
         sol = self.solver(x0=w0, lbx=self.lbu, ubx=self.ubu, lbg=self.lbg, ubg=self.ubg, p=params)

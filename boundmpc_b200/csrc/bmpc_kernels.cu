@@ -315,7 +315,11 @@ __global__ void __launch_bounds__(PREP_THREADS) k_finish(const __grid_constant__
     double* traj = io.post.traj + (size_t)b * C.N * TR_ROW;
     double* so = io.post.state_out + (size_t)b * PS_SIZE;
     if (ec < C.N) {
-      post_instance(C, io.post.tabs + (size_t)io.post.path_id[b] * io.post.J * PT_ROW, io.post.sector[b], st, w, ec, traj, so);
+      const double* tab = io.post.tabs + (size_t)io.post.path_id[b] * io.post.J * PT_ROW;
+      post_instance(C, tab, io.post.sector[b], st, w, ec, traj, so);
+      if (io.post.ref)      // logging branch (ref_data / err_data of BoundMPC.step), before the robot advance rewrites the joint state
+        log_instance(C, tab, io.post.sector[b], st, io.post.p + (size_t)b * C.np, traj, ec, so + PS_PRREF,
+                     io.post.ref + (size_t)b * C.N * RF_ROW, io.post.err + (size_t)b * C.N * ER_ROW);
       if (io.advance) advance_state(w, ec, traj, so);
     } else {                                       // the controller gives up (BoundMPC.py:504-506): nothing to return
       for (int i = 0; i < C.N * TR_ROW; i++) traj[i] = 0.0;
@@ -497,6 +501,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->single_pass = getenv("BMPC_SINGLE_PASS") != nullptr;
   h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
   if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
+  if (const char* e_ = getenv("BMPC_MAX_SOC")) h->C.max_soc = atoi(e_) > 0 ? 1 : 0;
   h->dbuf = nullptr; h->dbuf_bytes = 0;
   h->pin = nullptr; h->pin_bytes = 0;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -796,20 +801,94 @@ int bmpc_post_log_batch(bmpc_handle* h, int32_t batch, const double* path_tables
   return BMPC_OK;
 }
 
-int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
-                      const int32_t* sector, const double* state, const double* x, const double* g, const int32_t* status, double* prev_x,
-                      int32_t* error_count, double* traj, double* state_out, int32_t advance, void* cuda_stream) {
+static int finish_impl(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                       const int32_t* sector, const double* state, const double* x, const double* g, const int32_t* status, double* prev_x,
+                       int32_t* error_count, double* traj, double* state_out, int32_t advance, const double* p, double* ref, double* err,
+                       void* cuda_stream) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_finish_batch: null handle");
   if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !x || !g || !status || !prev_x ||
       !error_count || !traj || !state_out)
     return fail(BMPC_E_INVALID, "bmpc_finish_batch: invalid argument");
+  if (ref && (h->C.S < 3 || path_rows < 3 || !p || !err)) return fail(BMPC_E_INVALID, "bmpc_finish_batch: the logging branch needs p, err and nr_segs >= 3");
   if (batch == 0) return BMPC_OK;
   CU(cudaSetDevice(h->device));
-  FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out, nullptr, nullptr, nullptr}, g, status, prev_x,
-              error_count, advance};
+  FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out, ref ? p : nullptr, ref, ref ? err : nullptr}, g, status,
+              prev_x, error_count, advance};
   k_finish<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
   h->launches += 1;
+  return BMPC_OK;
+}
+
+int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows, const int32_t* path_id,
+                      const int32_t* sector, const double* state, const double* x, const double* g, const int32_t* status, double* prev_x,
+                      int32_t* error_count, double* traj, double* state_out, int32_t advance, void* cuda_stream) {
+  return finish_impl(h, batch, path_tables, n_paths, path_rows, path_id, sector, state, x, g, status, prev_x, error_count, traj, state_out, advance,
+                     nullptr, nullptr, nullptr, cuda_stream);
+}
+
+// One whole MPC step for `batch` controllers held on the host: k_prepare -> k_solve -> k_finish (+ logging branch) on the
+// handle's stream, inputs and outputs staged through ONE page-locked block each way.
+int bmpc_mpc_step_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                             const int32_t* path_id, int32_t* sector, const double* state, double* prev_x, int32_t* error_count,
+                             double* x, double* traj, double* state_out, double* ref, double* err, int32_t* iters, int32_t* status) {
+  if (!h) return fail(BMPC_E_INVALID, "bmpc_mpc_step_batch_host: null handle");
+  if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !prev_x || !error_count || !x || !traj ||
+      !state_out || !iters || !status || (ref && !err))
+    return fail(BMPC_E_INVALID, "bmpc_mpc_step_batch_host: invalid argument");
+  if (h->C.S > PREP_SMAX) return fail(BMPC_E_INVALID, "bmpc_mpc_step_batch_host: nr_segs above the builder's limit");
+  if (batch == 0) return BMPC_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np, N = h->C.N, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
+  size_t wsb = 0;
+  bmpc_workspace_bytes(h, batch, &wsb);
+  // block layout, identical in the page-locked staging area and on the device: [inputs | outputs | device-only scratch]
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_t = take(tb), o_id = take(B * 4), o_st = take(B * PS_SIZE * 8);
+  const size_t o_sec = take(B * 4), o_ec = take(B * 4), o_prev = take(B * n * 8);           // in / out
+  const size_t in_end = off;
+  const size_t o_x = take(B * n * 8), o_tr = take(B * N * TR_ROW * 8), o_so = take(B * PS_SIZE * 8), o_rf = take(ref ? B * N * RF_ROW * 8 : 8),
+               o_er = take(ref ? B * N * ER_ROW * 8 : 8), o_it = take(B * 4), o_stt = take(B * 4);
+  const size_t io_end = off;
+  const size_t o_x0 = take(B * n * 8), o_p = take(B * np * 8), o_g = take(B * m * 8), o_lg = take(B * m * 8), o_lx = take(B * n * 8), o_f = take(B * 8),
+               o_k = take(B * 8), o_ws = take(wsb);
+  int rc = ensure_dbuf(h, off);
+  if (rc) return rc;
+  rc = ensure_pin(h, io_end);
+  if (rc) return rc;
+  char* d = (char*)h->dbuf;
+  char* q = (char*)h->pin;
+  cudaStream_t st = h->stream;
+  memcpy(q + o_t, path_tables, tb);
+  memcpy(q + o_id, path_id, B * 4);
+  memcpy(q + o_st, state, B * PS_SIZE * 8);
+  memcpy(q + o_sec, sector, B * 4);
+  memcpy(q + o_ec, error_count, B * 4);
+  memcpy(q + o_prev, prev_x, B * n * 8);
+  CU(cudaMemcpyAsync(d, q, in_end, cudaMemcpyHostToDevice, st));
+  rc = bmpc_prepare_batch(h, batch, (double*)(d + o_t), n_paths, path_rows, (int32_t*)(d + o_id), (int32_t*)(d + o_sec), (double*)(d + o_st),
+                          (double*)(d + o_prev), (double*)(d + o_x0), (double*)(d + o_p), st);
+  if (rc) return rc;
+  rc = solve_batch_impl(h, batch, (double*)(d + o_x0), (double*)(d + o_p), (double*)(d + o_x), (double*)(d + o_g), (double*)(d + o_lg),
+                        (double*)(d + o_lx), (double*)(d + o_f), (int32_t*)(d + o_it), (int32_t*)(d + o_stt), (double*)(d + o_k), d + o_ws, st,
+                        nullptr, nullptr);
+  if (rc) return rc;
+  rc = finish_impl(h, batch, (double*)(d + o_t), n_paths, path_rows, (int32_t*)(d + o_id), (int32_t*)(d + o_sec), (double*)(d + o_st),
+                   (double*)(d + o_x), (double*)(d + o_g), (int32_t*)(d + o_stt), (double*)(d + o_prev), (int32_t*)(d + o_ec), (double*)(d + o_tr),
+                   (double*)(d + o_so), 0, (double*)(d + o_p), ref ? (double*)(d + o_rf) : nullptr, ref ? (double*)(d + o_er) : nullptr, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(q + o_sec, d + o_sec, io_end - o_sec, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(sector, q + o_sec, B * 4);
+  memcpy(error_count, q + o_ec, B * 4);
+  memcpy(prev_x, q + o_prev, B * n * 8);
+  memcpy(x, q + o_x, B * n * 8);
+  memcpy(traj, q + o_tr, B * N * TR_ROW * 8);
+  memcpy(state_out, q + o_so, B * PS_SIZE * 8);
+  if (ref) { memcpy(ref, q + o_rf, B * N * RF_ROW * 8); memcpy(err, q + o_er, B * N * ER_ROW * 8); }
+  memcpy(iters, q + o_it, B * 4);
+  memcpy(status, q + o_stt, B * 4);
   return BMPC_OK;
 }
 

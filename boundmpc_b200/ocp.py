@@ -60,6 +60,7 @@ class BatchSolver:
         self.tol = cfg.tol
         self._stats = {"iter_count": 0, "success": False, "return_status": "unset"}
         self._ws = None
+        self._bounds = None
 
     def __del__(self):
         try:
@@ -78,7 +79,26 @@ class BatchSolver:
         return lbx, ubx, lbg, ubg
 
     # ---- CasADi-like single solve (BoundMPC.py:446-453)
+    def set_stats(self, iters, status, kkt=None):
+        self._stats = {"iter_count": int(iters), "success": int(status) == 0, "return_status": RETURN_STATUS.get(int(status), "Internal_Error")}
+        if kkt is not None:
+            self._stats["kkt_error"] = float(kkt)
+
+    def _check_bounds(self, **given):
+        """The bound vectors are constants of the handle (bmpc_bounds = what setup_optimization_problem returned); a caller
+        that passes different ones would silently get the wrong problem solved, so that is an error."""
+        if self._bounds is None:
+            self._bounds = dict(zip(("lbx", "ubx", "lbg", "ubg"), self.bounds()))
+        for k, v in given.items():
+            if v is None:
+                continue
+            a = np.asarray(v, float).ravel()
+            if a.shape != self._bounds[k].shape or not np.array_equal(a, self._bounds[k]):
+                raise ValueError(f"{k} differs from the bounds this solver was built with (setup_optimization_problem); "
+                                 "the B200 solver has them compiled into the handle")
+
     def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_g0=None, lam_x0=None):
+        self._check_bounds(lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
         out = self.solve_batch(np.asarray(x0, float).reshape(1, -1), np.asarray(p, float).reshape(1, -1))
         st = int(out["status"][0])
         self._stats = {"iter_count": int(out["iters"][0]), "success": st == 0,
@@ -132,6 +152,11 @@ class BatchSolver:
         kkt = o.get("kkt") if "kkt" in o else np.empty(B)
         it = o.get("iters") if "iters" in o else np.empty(B, np.int32)
         st = o.get("status") if "status" in o else np.empty(B, np.int32)
+        for name, a, shape, dt in (("x", x, (B, self.n), np.float64), ("g", g, (B, self.m), np.float64), ("lam_g", lg, (B, self.m), np.float64),
+                                   ("lam_x", lx, (B, self.n), np.float64), ("f", f, (B,), np.float64), ("kkt", kkt, (B,), np.float64),
+                                   ("iters", it, (B,), np.int32), ("status", st, (B,), np.int32)):
+            if not isinstance(a, np.ndarray) or a.dtype != dt or a.shape != shape or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"solve_batch: out['{name}'] must be a C-contiguous {np.dtype(dt).name} array of shape {shape}")
         P = _cabi.ptr
         _cabi.check(self._lib.bmpc_solve_batch_host(self._h, B, P(x0), P(p), P(x), P(g), P(lg), P(lx), P(f), P(it), P(st), P(kkt)),
                     "bmpc_solve_batch_host")
@@ -300,6 +325,33 @@ class BatchSolver:
                                                 V(error_count.data_ptr()), V(traj.data_ptr()), V(so.data_ptr()), int(bool(advance)),
                                                 V(stream)), "bmpc_finish_batch")
         return {"traj": traj, "state": so}
+
+
+    def mpc_step_host(self, tables, path_id, sector, state, prev_x, error_count, want_log=True):
+        """One whole MPC step (`BoundMPC.step`: prepare -> solve -> accept / fallback -> post-processing [+ logging branch]) for B
+        controllers whose state lives on the host, in ONE library call (`bmpc_mpc_step_batch_host`).  numpy arrays: tables
+        [P, J, 41], path_id / sector / error_count [B] int32, state [B, 76], prev_x [B, n].  Returns dict x, traj [B, N, 42],
+        state [B, 76] (next step), ref [B, N, 55] / err [B, N, 33] (or None), iters, status, and the updated sector, prev,
+        error_count."""
+        tables = np.ascontiguousarray(tables, np.float64)
+        state = np.ascontiguousarray(state, np.float64)
+        B = state.shape[0]
+        pid = np.ascontiguousarray(path_id, np.int32)
+        sec = np.array(sector, np.int32).reshape(B).copy()
+        ec = np.array(error_count, np.int32).reshape(B).copy()
+        prev = np.array(prev_x, np.float64).reshape(B, self.n).copy()
+        if tables.ndim != 3 or tables.shape[2] != self.PT_ROW or state.shape != (B, self.PS_SIZE):
+            raise ValueError("mpc_step_host: unexpected array shapes")
+        x, traj, so = np.empty((B, self.n)), np.empty((B, self.N, self.TR_ROW)), np.empty((B, self.PS_SIZE))
+        ref = np.empty((B, self.N, self.RF_ROW)) if want_log else None
+        err = np.empty((B, self.N, self.ER_ROW)) if want_log else None
+        it, st = np.empty(B, np.int32), np.empty(B, np.int32)
+        P = _cabi.ptr
+        _cabi.check(self._lib.bmpc_mpc_step_batch_host(self._h, B, P(tables), tables.shape[0], tables.shape[1], P(pid), P(sec), P(state),
+                                                       P(prev), P(ec), P(x), P(traj), P(so), P(ref), P(err), P(it), P(st)),
+                    "bmpc_mpc_step_batch_host")
+        return {"x": x, "traj": traj, "state": so, "ref": ref, "err": err, "iters": it, "status": st, "sector": sec, "prev": prev,
+                "error_count": ec}
 
     # ---- NLP function evaluation for parity tests (nlp_f / nlp_g / nlp_grad_f / nlp_jac_g / nlp_hess_l)
     def eval_batch(self, x, p, lam=None, want_jac=True, want_hess=True):

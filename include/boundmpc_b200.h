@@ -164,6 +164,18 @@ int bmpc_finish_batch(bmpc_handle* h, int32_t batch, const double* path_tables, 
                       const int32_t* path_id, const int32_t* sector, const double* state, const double* x, const double* g,
                       const int32_t* status, double* prev_x, int32_t* error_count, double* traj, double* state_out,
                       int32_t advance, void* cuda_stream);
+/* One whole MPC step — `BoundMPC.step` (BoundMPC.py:306-506,508-770) — for `batch` controllers whose state the caller holds on
+ * the HOST (the single controller of bound_mpc_node.py is batch = 1): bmpc_prepare_batch, bmpc_solve_batch and bmpc_finish_batch
+ * (advance = 0) back to back on the handle's stream, one staged copy each way, one synchronisation.
+ *   path_tables, path_id, state          as for bmpc_prepare_batch
+ *   sector, prev_x, error_count          in / out (window position, previous solution, BoundMPC.error_count)
+ *   x        [batch, n]                  the solver's solution of this step (kept or not, see status / error_count)
+ *   traj     [batch, N, 42], state_out [batch, 76]   as for bmpc_post_batch, for the trajectory the controller keeps
+ *   ref [batch, N, 55], err [batch, N, 33] or NULL, NULL   logging branch, as for bmpc_post_log_batch
+ *   iters, status [batch]                solver statistics (stats()['iter_count'], status == 0 <=> stats()['success']) */
+int bmpc_mpc_step_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
+                             const int32_t* path_id, int32_t* sector, const double* state, double* prev_x, int32_t* error_count,
+                             double* x, double* traj, double* state_out, double* ref, double* err, int32_t* iters, int32_t* status);
 /* bmpc_post_batch with HOST pointers (copies inside, synchronises). */
 int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                          const int32_t* path_id, const int32_t* sector, const double* state, const double* w,

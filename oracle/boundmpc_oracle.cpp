@@ -9,7 +9,8 @@
 //   * the solve behind `self.solver(x0, lbx, ubx, lbg, ubg, p)` (BoundMPC.py:446-457):
 //     a primal-dual interior-point method in Ipopt's formulation (slacks for the inequality
 //     rows, log barriers with multipliers for bounds, fraction-to-boundary, filter line
-//     search, inertia correction by Hessian perturbation; Wächter & Biegler 2006 — the
+//     search with second-order correction, barrier decrease globalised by the kkt-error
+//     progress test, inertia correction by Hessian perturbation; Wächter & Biegler 2006 — the
 //     published algorithm of Ipopt 3.x, pulled in unpinned through `casadi`,
 //     bound_mpc/requirements.txt:1).  The symmetric indefinite KKT system MUMPS factorises
 //     is solved here by a stage-wise Riccati recursion (same Newton step).
@@ -304,12 +305,10 @@ struct Opts {
   double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta_sw = 1.0;
   int verbose = 0;
   double diverge_tol = 1e7;   // dual infeasibility beyond which the multipliers are taken to diverge (locally infeasible instance)
-  int mu_strategy = 3;        // 0: monotone; 3 (default, = the CUDA path): monotone + kkt-error progress test with re-centring;
-                              // experiments: 1 adaptive with the LOQO oracle, 2 adaptive with a quality-function oracle
-  int zinit = 0;              // 0: z = mu_init / slack, 1: z = mu_init (Ipopt warm_start_mult_bound_push)
-  double mu_min = 1e-11, mu_max_fact = 1e3;
-  double rz_kappa = 0; int red_iters = 3; int single_dec = 1; int max_soc = 1;
-  double boost_thr = 0, boost_fac = 10, boost_cap = 1.0; int boost_hold = 0;
+  int mu_strategy = 3;        // 3 (default, = the CUDA path): monotone decrease + kkt-error progress test with re-centring; 0: monotone only
+  int red_iters = 3;          // progress test: no improvement on any of the last red_iters accepted iterates ...
+  double boost_fac = 10, boost_cap = 1.0;   // ... -> mu <- min(cap, fac * mu)
+  int max_soc = 1;            // second-order corrections per iteration
 };
 
 struct Ipm {
@@ -602,21 +601,17 @@ struct Ipm {
       eval_values(P, x.data(), p, f, g.data(), d.data());
       for (int i = 0; i < ni; i++) s[i] = std::max(-d[i], o.bound_push);
     }
-    for (int i = 0; i < ni; i++) zs[i] = o.zinit ? mu : mu / s[i];
+    for (int i = 0; i < ni; i++) zs[i] = mu / s[i];
     for (int i = 0; i < n; i++) {
-      zL[i] = std::isfinite(lbx[i]) ? (o.zinit ? mu : mu / (x[i] - lbx[i])) : 0.0;
-      zU[i] = std::isfinite(ubx[i]) ? (o.zinit ? mu : mu / (ubx[i] - x[i])) : 0.0;
+      zL[i] = std::isfinite(lbx[i]) ? mu / (x[i] - lbx[i]) : 0.0;
+      zU[i] = std::isfinite(ubx[i]) ? mu / (ubx[i] - x[i]) : 0.0;
     }
     filter.clear();
     double theta0 = -1, theta_max = 0, theta_min = 0;
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
     int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
-    bool free_mode = true, ls_skipped = false, continue_flag = false;
     int n_soc = 0;
-    double qf_avg = 0, qf_d = 0, qf_p = 0;
-    int boost_wait = 0;
-    double mu_max = -1;
     std::vector<double> refs;
     for (;; it++) {
       pack_lam();
@@ -629,19 +624,19 @@ struct Ipm {
       if (it >= o.max_iter) { status = 1; break; }
       if (parts[0] > o.diverge_tol) { status = 5; break; }
       // barrier parameter
-      if (o.mu_strategy == 0 || o.mu_strategy == 3) {
-        // monotone Fiacco-McCormick, Ipopt eq. (7)
+      {
+        // monotone Fiacco-McCormick decrease (Waechter & Biegler 2006, eq. (7)), one level per iteration
         bool mu_changed = false;
-        while (mu > o.tol / 10 && kkt_error(mu) <= o.kappa_eps * mu) {
+        if (mu > o.tol / 10 && kkt_error(mu) <= o.kappa_eps * mu) {
           mu = std::max(o.tol / 10, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
           mu_changed = true;
-          if (o.single_dec) break;
         }
         if (mu_changed) { filter.clear(); refs.clear(); }
         if (o.mu_strategy == 3) {
-          // progress monitor (Ipopt's kkt-error globalisation test, adaptive_mu_kkterror_red_iters = 4): when the optimality
-          // error has not improved on any of the last four iterates the iteration is crawling along the boundary
-          // (fraction-to-the-boundary cuts); re-centre at a larger barrier parameter
+          // progress test of Ipopt's adaptive strategy (adaptive_mu_globalization = kkt-error, the reference's setting,
+          // BoundMPC.py:130-131; here with red_iters = 3): when the optimality error has not improved on any of the last
+          // red_iters accepted iterates the iteration is crawling along the boundary (a slack pinned at zero by a grown
+          // multiplier, every step cut by the fraction-to-the-boundary rule); re-centre at a larger barrier parameter
           double parts2[3];
           const double qf = kkt_error(0.0, parts2);
           bool suff = true;
@@ -652,58 +647,6 @@ struct Ipm {
             filter.clear(); refs.clear();
             if (o.verbose) printf("      no progress: mu -> %.3e\n", mu);
           }
-        }
-      } else {
-        // adaptive: Ipopt's AdaptiveMuUpdate with the LOQO oracle and kkt-error globalisation
-        double csum = 0, cmin = 1e300, q_d = 0, q_p = 0, q_c = 0; int nc = 0;
-        for (int i = 0; i < ni; i++) { double c = s[i] * zs[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
-        for (int i = 0; i < n; i++) {
-          if (std::isfinite(lbx[i])) { double c = (x[i] - lbx[i]) * zL[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
-          if (std::isfinite(ubx[i])) { double c = (ubx[i] - x[i]) * zU[i]; csum += c; cmin = std::min(cmin, c); q_c += c * c; nc++; }
-        }
-        const double avg = csum / nc, xi = cmin / avg;
-        {
-          std::vector<double> r; dual_residual(y, zs, r);
-          for (int i = 0; i < n; i++) q_d += r[i] * r[i];
-          for (int k = 0; k < N; k++) {
-            for (int i = 0; i < NE; i++) q_p += E.g[NG * k + i] * E.g[NG * k + i];
-            for (int i = 0; i < ND; i++) { double v = E.d[ND * k + i] + s[ND * k + i]; q_p += v * v; }
-          }
-        }
-        const double qf = q_d / n + q_p / (ne + ni) + q_c / nc;
-        qf_avg = avg; qf_d = q_d / n; qf_p = q_p / (ne + ni);
-        if (mu_max < 0) mu_max = o.mu_max_fact * avg;
-        bool suff = true;
-        if ((int)refs.size() >= 4) { suff = false; for (double r : refs) if (qf <= 0.9999 * r) suff = true; }
-        auto remember = [&]() { if ((int)refs.size() >= 4) refs.erase(refs.begin()); refs.push_back(qf); };
-        if (!free_mode) {
-          if (suff) { free_mode = true; remember(); }
-          else if (kkt_error(mu) <= o.kappa_eps * mu) {
-            mu = std::max(o.mu_min, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
-            filter.clear();
-          }
-        } else {
-          if (ls_skipped) suff = false;
-          if (suff) remember();
-          else { free_mode = false; mu = std::min(mu_max, std::max(o.mu_min, 0.8 * avg)); filter.clear(); }
-        }
-        if (free_mode && o.mu_strategy == 1) {
-          const double fac = 0.05 * (1 - xi) / xi;
-          const double sigma = 0.1 * std::pow(std::min(fac, 2.0), 3);
-          mu = std::min(mu_max, std::max(o.mu_min, sigma * avg));
-          filter.clear();
-        }
-        if (o.verbose) printf("      adaptive: free %d avg %.3e xi %.3e qf %.3e -> mu %.3e\n", (int)free_mode, avg, xi, qf, mu);
-      }
-      if (o.rz_kappa > 0) {
-        // infeasibility-aware floor of the barrier parameter: a violated inequality row (d + s > 0) whose multiplier has grown
-        // pins its slack at zero, and the fraction-to-the-boundary rule then cuts every step to a crawl; re-centre so that the
-        // barrier keeps that slack away from zero while the row is being made feasible
-        double mrz = 0;
-        for (int i = 0; i < ni; i++) mrz = std::max(mrz, (E.d[i] + s[i]) * zs[i]);
-        if (o.rz_kappa * mrz > mu) {
-          mu = std::min(o.boost_cap, o.rz_kappa * mrz); filter.clear();
-          if (o.verbose) printf("      rz floor: mu -> %.3e\n", mu);
         }
       }
       double th_cur = theta(E.g.data(), E.d.data(), s);
@@ -741,54 +684,8 @@ struct Ipm {
           if (std::isfinite(ubx[i])) { double su = ubx[i] - x[i]; dzU[i] = gc / su - ga * zU[i] + zU[i] / su * dx[i]; }
         }
       };
-      if (o.mu_strategy == 2 && free_mode) {
-        // quality-function oracle (Ipopt's QualityFunctionMuOracle): the step is affine in mu, step(mu) = step_a + mu step_c
-        if (!factor_solve(1, 0, 1)) { status = 3; break; }
-        rest_of_step(1, 0);
-        std::vector<double> ax = dx, as = ds, ay = ynew, azs = dzs, azL = dzL, azU = dzU;
-        if (!riccati(dw, 0, 1, 0)) { status = 3; break; }
-        rest_of_step(0, 1);
-        std::vector<double> cx = dx, cs_ = ds, cy = ynew, czs = dzs, czL = dzL, czU = dzU;
-        const double avg = qf_avg;
-        auto qf = [&](double muc) {
-          const double tauq = std::max(o.tau_min, 1 - muc);
-          double ap = 1, ad = 1;
-          for (int i = 0; i < ni; i++) {
-            double d1 = as[i] + muc * cs_[i], d2 = azs[i] + muc * czs[i];
-            if (d1 < 0) ap = std::min(ap, -tauq * s[i] / d1);
-            if (d2 < 0) ad = std::min(ad, -tauq * zs[i] / d2);
-          }
-          for (int i = 0; i < n; i++) {
-            double d1 = ax[i] + muc * cx[i];
-            if (std::isfinite(lbx[i])) { double d2 = azL[i] + muc * czL[i]; if (d1 < 0) ap = std::min(ap, -tauq * (x[i] - lbx[i]) / d1); if (d2 < 0) ad = std::min(ad, -tauq * zL[i] / d2); }
-            if (std::isfinite(ubx[i])) { double d2 = azU[i] + muc * czU[i]; if (d1 > 0) ap = std::min(ap, tauq * (ubx[i] - x[i]) / d1); if (d2 < 0) ad = std::min(ad, -tauq * zU[i] / d2); }
-          }
-          double qc = 0; int nc = 0;
-          for (int i = 0; i < ni; i++) { double v = (s[i] + ap * (as[i] + muc * cs_[i])) * (zs[i] + ad * (azs[i] + muc * czs[i])); qc += v * v; nc++; }
-          for (int i = 0; i < n; i++) {
-            double d1 = ax[i] + muc * cx[i];
-            if (std::isfinite(lbx[i])) { double v = (x[i] - lbx[i] + ap * d1) * (zL[i] + ad * (azL[i] + muc * czL[i])); qc += v * v; nc++; }
-            if (std::isfinite(ubx[i])) { double v = (ubx[i] - x[i] - ap * d1) * (zU[i] + ad * (azU[i] + muc * czU[i])); qc += v * v; nc++; }
-          }
-          return (1 - ad) * (1 - ad) * qf_d + (1 - ap) * (1 - ap) * qf_p + qc / nc;
-        };
-        double best = 1e300, bs = 1;
-        for (double lg = -6; lg <= 2.001; lg += 0.5) {
-          const double sg = std::pow(10.0, lg);
-          const double muc = std::min(mu_max, std::max(o.mu_min, sg * avg));
-          const double q = qf(muc);
-          if (q < best) { best = q; bs = muc; }
-        }
-        mu = bs;
-        filter.clear();
-        if (o.verbose) printf("      qf oracle: avg %.3e -> mu %.3e (sigma %.3g)\n", avg, mu, mu / avg);
-        for (int i = 0; i < n; i++) { dx[i] = ax[i] + mu * cx[i]; dzL[i] = azL[i] + mu * czL[i]; dzU[i] = azU[i] + mu * czU[i]; }
-        for (int i = 0; i < ni; i++) { ds[i] = as[i] + mu * cs_[i]; dzs[i] = azs[i] + mu * czs[i]; }
-        for (int i = 0; i < ne; i++) ynew[i] = ay[i] + mu * cy[i];
-      } else {
-        if (!factor_solve(1, mu, 1)) { status = 3; break; }
-        rest_of_step(1, mu);
-      }
+      if (!factor_solve(1, mu, 1)) { status = 3; break; }
+      rest_of_step(1, mu);
       if (o.verbose > 1) printf("      delta_w %.1e lin_res %.2e\n", dw, lin_residual());
       // fraction to the boundary
       double tau = std::max(o.tau_min, 1 - mu), apr = 1, adu = 1;
@@ -891,13 +788,11 @@ struct Ipm {
           dx = dx0; ds = ds0; ynew = y0; dzs = dzs0; dzL = dzL0; dzU = dzU0;
         }
       }
-      ls_skipped = false;
       if (!accepted) {
         // no restoration phase: clear the filter and take the damped step that keeps the iterate interior
         filter.clear();
         alpha = apr * std::pow(0.5, 6);
         if (o.verbose) printf("      line search failed; damped step\n");
-        ls_skipped = true;
         if (++ls_fail > 8) { status = 2; break; }
       } else if (!ftype) {
         filter.push_back({(1 - o.gamma_theta) * th_cur, phi_cur - o.gamma_phi * th_cur});
@@ -921,13 +816,6 @@ struct Ipm {
         if (std::isfinite(lbx[i])) { double sl = x[i] - lbx[i]; zL[i] += adu * dzL[i]; zL[i] = std::max(std::min(zL[i], ks * mu / sl), mu / (ks * sl)); }
         if (std::isfinite(ubx[i])) { double su = ubx[i] - x[i]; zU[i] += adu * dzU[i]; zU[i] = std::max(std::min(zU[i], ks * mu / su), mu / (ks * su)); }
       }
-      if (o.boost_thr > 0 && apr < o.boost_thr && mu < o.boost_cap && boost_wait <= 0) {
-        // badly centred iterate: the fraction-to-the-boundary rule cuts Newton's step to a crawl; re-centre at a larger barrier parameter
-        mu = std::min(o.boost_cap, mu * o.boost_fac);
-        filter.clear();
-        boost_wait = o.boost_hold;
-        if (o.verbose) printf("      boost mu -> %.3e (apr %.3e)\n", mu, apr);
-      } else boost_wait--;
     }
     iters = it;
     return status;
@@ -956,6 +844,13 @@ int orc_bounds(int N, int S, double dt, double* lbx, double* ubx, double* lbg, d
 int orc_eval(int N, int S, double dt, const double* x, const double* p, double* f, double* g) {
   Prob P(N, S, dt);
   eval_values(P, x, p, *f, g);
+  return 0;
+}
+
+// values with the interval-form inequality rows d [12 N] (the form the iteration works on)
+int orc_eval_d(int N, int S, double dt, const double* x, const double* p, double* f, double* g, double* d) {
+  Prob P(N, S, dt);
+  eval_values(P, x, p, *f, g, d);
   return 0;
 }
 
@@ -1037,7 +932,7 @@ int orc_derivs_interval(int N, int S, double dt, const double* x, const double* 
 }
 
 static thread_local double* g_trace; static thread_local int g_trace_cap;
-// opts: [tol, max_iter, mu_init, bound_push, verbose]
+// opts: [tol, max_iter, mu_init, bound_push, verbose, mu_strategy (< 0: default), max_soc (< 0: default)]
 int orc_solve(int N, int S, double dt, const double* x0, const double* p, const double* opts,
               double* x, double* g, double* lam_g, double* lam_x, double* f, int* iters, double* kkt) {
   Prob P(N, S, dt);
@@ -1049,19 +944,8 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
     if (opts[3] > 0) o.bound_push = opts[3];
     o.verbose = (int)opts[4];
   }
-  if (const char* e = getenv("ORC_MU")) o.mu_strategy = atoi(e);
-  if (const char* e = getenv("ORC_ZINIT")) o.zinit = atoi(e);
-  if (const char* e = getenv("ORC_KEPS")) o.kappa_eps = atof(e);
-  if (const char* e = getenv("ORC_KMU")) o.kappa_mu = atof(e);
-  if (const char* e = getenv("ORC_TMU")) o.theta_mu = atof(e);
-  if (const char* e = getenv("ORC_SOC")) o.max_soc = atoi(e);
-  if (const char* e = getenv("ORC_SINGLE")) o.single_dec = atoi(e);
-  if (const char* e = getenv("ORC_RED")) o.red_iters = atoi(e);
-  if (const char* e = getenv("ORC_RZ")) o.rz_kappa = atof(e);
-  if (const char* e = getenv("ORC_BTHR")) o.boost_thr = atof(e);
-  if (const char* e = getenv("ORC_BFAC")) o.boost_fac = atof(e);
-  if (const char* e = getenv("ORC_BCAP")) o.boost_cap = atof(e);
-  if (const char* e = getenv("ORC_BHOLD")) o.boost_hold = atoi(e);
+  if (opts && opts[5] >= 0) o.mu_strategy = (int)opts[5];
+  if (opts && opts[6] >= 0) o.max_soc = (int)opts[6];
   Ipm ipm(P, p, o);
   ipm.trace = g_trace; ipm.trace_cap = g_trace_cap;
   int it = 0;

@@ -63,11 +63,11 @@ def derivs(x, p, lam, N=10, S=4, dt=0.1):
     return grad, jac, hess
 
 
-def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=1e-3, bound_push=1e-3, verbose=0):
+def solve(x0, p, N=10, S=4, dt=0.1, tol=1e-8, max_iter=500, mu_init=1e-3, bound_push=1e-3, verbose=0, mu_strategy=-1, max_soc=-1):
     n, m, _ = dims(N, S)
     x0 = np.ascontiguousarray(x0, float)
     p = np.ascontiguousarray(p, float)
-    opts = np.array([tol, max_iter, mu_init, bound_push, verbose], float)
+    opts = np.array([tol, max_iter, mu_init, bound_push, verbose, mu_strategy, max_soc], float)
     x, g, lam_g, lam_x = np.empty(n), np.empty(m), np.empty(m), np.empty(n)
     f, it, kkt = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
     st = lib().orc_solve(N, S, ctypes.c_double(dt), _p(x0), _p(p), _p(opts), _p(x), _p(g), _p(lam_g), _p(lam_x),
@@ -84,3 +84,38 @@ def derivs_interval(x, p, lam, N=10, S=4, dt=0.1):
     d, grad, jac, hess = np.empty(12 * N), np.empty(n), np.empty((48 * N, n)), np.empty((n, n))
     lib().orc_derivs_interval(N, S, ctypes.c_double(dt), _p(x), _p(p), _p(lam), _p(d), _p(grad), _p(jac), _p(hess))
     return d, grad, jac, hess
+
+
+class OracleSolver:
+    """The solver call surface (`solver(x0=, p=)`, `stats()`, `bounds()`, `eval_batch(...)['d']`) on top of the CPU oracle.
+    Used by bench.py's reference arm to generate its inputs without touching the CUDA library (boundmpc_b200.batches
+    needs a solver for the nominal closed loops and for the bound-excess probe of its repaired generator)."""
+
+    def __init__(self, N=10, nr_segs=4, dt=0.1, tol=1e-9):
+        self.N, self.nr_segs, self.dt, self.tol = N, nr_segs, dt, tol
+        self.n, self.m, self.np = dims(N, nr_segs)
+        self._stats = {}
+
+    def bounds(self):
+        return bounds(self.N, self.nr_segs, self.dt)
+
+    def __call__(self, x0=None, p=None, **kw):
+        r = solve(np.asarray(x0, float).ravel(), np.asarray(p, float).ravel(), self.N, self.nr_segs, self.dt, tol=self.tol)
+        self._stats = dict(iter_count=int(r["iters"]), success=r["status"] == 0, return_status=str(r["status"]))
+        return dict(x=r["x"], g=r["g"], lam_g=r["lam_g"], lam_x=r["lam_x"], f=r["f"])
+
+    def stats(self):
+        return dict(self._stats)
+
+    def generate_dependencies(self, *a, **k):
+        return None
+
+    def eval_batch(self, x, p, lam=None, want_jac=False, want_hess=False):
+        """Interval-form inequality rows d [B, 12 N] (all the batch generator reads)."""
+        x, p = np.atleast_2d(x), np.atleast_2d(p)
+        d = np.empty((len(x), 12 * self.N))
+        g, f = np.empty(self.m), ctypes.c_double()
+        for i in range(len(x)):
+            xi, pi = np.ascontiguousarray(x[i], float), np.ascontiguousarray(p[i], float)
+            lib().orc_eval_d(self.N, self.nr_segs, ctypes.c_double(self.dt), _p(xi), _p(pi), ctypes.byref(f), _p(g), _p(d[i]))
+        return {"d": d}

@@ -29,3 +29,25 @@ class EmuSolver:
 
     def generate_dependencies(self, *a, **k):
         return None
+
+    # serial form of bmpc_mpc_step_batch_host (k_prepare -> k_solve -> k_finish + logging branch), same return dict as
+    # BatchSolver.mpc_step_host: lets the CPU suite drive BoundMPC's device step
+    def mpc_step_host(self, tables, path_id, sector, state, prev_x, error_count, want_log=True):
+        state = np.ascontiguousarray(np.atleast_2d(state), float)
+        B = state.shape[0]
+        prev = np.array(prev_x, float).reshape(B, self.n).copy()
+        ec = np.array(error_count, np.int32).reshape(B).copy()
+        x0, p, sec = emu.prepare(tables, path_id, sector, state, prev, self.N, self.nr_segs)
+        r = emu.solve(x0, p, self.N, self.nr_segs, self.dt, self.tol)
+        kept_prev = prev.copy()
+        traj, so, prev, ec_out = emu.finish(tables, path_id, sec, state, r["x"], r["g"], r["status"], prev, ec, advance=False, N=self.N,
+                                            S=self.nr_segs, dt=self.dt)
+        ref = err = None
+        if want_log:
+            w = np.where((ec_out == 0)[:, None], r["x"], kept_prev)
+            _, _, ref, err = emu.post_log(tables, path_id, sec, state, p, w, ec_out, self.N, self.nr_segs, self.dt)
+        return {"x": r["x"], "traj": traj, "state": so, "ref": ref, "err": err, "iters": r["iters"], "status": r["status"], "sector": sec,
+                "prev": prev, "error_count": ec_out}
+
+    def set_stats(self, iters, status, kkt=None):
+        self._stats = dict(iter_count=int(iters), success=int(status) == 0, return_status=str(int(status)))
