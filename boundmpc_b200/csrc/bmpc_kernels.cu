@@ -99,7 +99,7 @@ __device__ int sched_next(const SchedMem& M, int batch, int* mode) {
 
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__ Config C0, int batch, BatchIO io, double* ws,
-                                                         size_t ws_stride, SchedMem M) {
+                                                         size_t ws_stride, SchedMem M, int vec_ext) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 #ifdef BMPC_TIMING
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
   if (threadIdx.x == 0) {
     S.cfg = C0;
     work_carve(S.work, ws + (size_t)blockIdx.x * ws_stride, C0.N);
-    work_attach_smem(S.work, S, C0.N);
+    work_attach_smem(S.work, S, C0.N, vec_ext ? reinterpret_cast<double*>(smem_raw + sizeof(Smem)) : nullptr);
   }
   __syncthreads();
 #ifdef BMPC_PROBE_SLOTS   // development aid (scripts/probe_slots.py): SM and hardware warp slots of a few CTAs
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
 }
 
 // launch variants: (threads per CTA, resident CTAs per SM the register budget is compiled for)
-typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, SchedMem);
+typedef void (*solve_fn)(const Config, int, BatchIO, double*, size_t, SchedMem, int);
 struct SolveVariant { int threads, minb; solve_fn fn; };
 static const SolveVariant kVariants[] = {
 #ifdef BMPC_TIMING
@@ -414,6 +414,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 struct bmpc_handle {
   Config C;
   int device, threads, sms, ctas_per_sm, variant;
+  size_t smem_solve;   // dynamic shared memory of k_solve: sizeof(Smem) [+ the iterate of horizons above VEC_NMAX]
   int single_pass, no_zero_copy;   // development switches, read from the environment once in bmpc_create
   int variant_lat;     // launch shape for batches of at most one instance per SM (-1: none): more threads per instance
   size_t ws_stride;    // doubles per CTA slot
@@ -487,13 +488,20 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     for (int v = 0; v < kNumVariants; v++)
       if (kVariants[v].threads == 384 && kVariants[v].minb == 1) h->variant_lat = v;
   e = cudaSuccess;
-  if (h->variant_lat >= 0) e = cudaFuncSetAttribute(kVariants[h->variant_lat].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  // horizons above VEC_NMAX: the iterate (N x 192 doubles) goes behind the struct when two CTAs per SM still fit
+  // (BMPC_VEC_GLOBAL=1: leave it in the workspace, three CTAs per SM -- the trade-off is measured in DESIGN.md)
+  h->smem_solve = sizeof(Smem);
+  {
+    const size_t ext = (size_t)h->C.N * (3 * NX + NE + 2 * ND) * sizeof(double);
+    if (h->C.N > VEC_NMAX && !getenv("BMPC_VEC_GLOBAL") && 2 * (sizeof(Smem) + ext + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) h->smem_solve += ext;
+  }
+  if (h->variant_lat >= 0) e = cudaFuncSetAttribute(kVariants[h->variant_lat].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solve);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solve);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e != cudaSuccess) { delete h; return fail(BMPC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kVariants[h->variant].fn, h->threads, sizeof(Smem));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kVariants[h->variant].fn, h->threads, h->smem_solve);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(BMPC_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
   h->ctas_per_sm = want_c < occ ? want_c : occ;
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
@@ -547,7 +555,7 @@ int bmpc_launch_shape(const bmpc_handle* h, int32_t* threads, int32_t* ctas_per_
   if (!h) return fail(BMPC_E_INVALID, "bmpc_launch_shape: null handle");
   if (threads) *threads = h->threads;
   if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
-  if (smem_bytes) *smem_bytes = (int32_t)sizeof(Smem);
+  if (smem_bytes) *smem_bytes = (int32_t)h->smem_solve;
   if (sms) *sms = h->sms;
   return BMPC_OK;
 }
@@ -613,7 +621,7 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
   }
   BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status, x0_src, p_src};
   const int v = (h->variant_lat >= 0 && batch <= h->sms) ? h->variant_lat : h->variant;
-  kVariants[v].fn<<<grid, kVariants[v].threads, sizeof(Smem), st>>>(h->C, batch, io, ws, h->ws_stride, M);
+  kVariants[v].fn<<<grid, kVariants[v].threads, h->smem_solve, st>>>(h->C, batch, io, ws, h->ws_stride, M, h->smem_solve > sizeof(Smem) ? 1 : 0);
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

@@ -67,7 +67,8 @@ struct Smem {
 // The blocks of the Riccati sweep are idle during the evaluation phases: the forward-kinematics scratch and the
 // path part of the stage records (both written lane by lane, i.e. as scattered 8-byte stores if they lived in
 // global memory) are placed there when they fit (N = 10: both; N = 20: the kinematics scratch only).
-BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N) {
+// (vec_ext: dynamic shared memory behind the Smem struct for the iterate of horizons above VEC_NMAX, or null)
+BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N, double* vec_ext = nullptr) {
   int used = 0;
   if (2 * N * F_SIZE <= EV_CAP) { W.fk = S.ev; used = 2 * N * F_SIZE; }
   if (used + N * R_PATH <= EV_CAP) { W.prec = S.ev + used - R_HY; W.prec_stride = R_PATH; }
@@ -81,6 +82,12 @@ BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N) {
     q = S.ev + EV_STEP0;
     W.dx = q; q += n; W.dzL = q; q += n; W.dzU = q; q += n; W.xt = q; q += n; W.ynew = q; q += ne; W.ct = q; q += ne;
     W.ds = q; q += nd; W.dzs = q; q += nd; W.st = q; q += nd; W.dtr = q; q += nd;
+  } else if (vec_ext) {
+    // longer horizons (N = 20: 30 KB): the iterate alone, in the dynamic shared memory behind the struct (two CTAs per SM
+    // instead of three); the step / trial vectors stay in the workspace
+    const int n = NX * N, ne = NE * N, nd = ND * N;
+    double* q = vec_ext;
+    W.x = q; q += n; W.zL = q; q += n; W.zU = q; q += n; W.y = q; q += ne; W.s = q; q += nd; W.zs = q; q += nd;
   }
 }
 

@@ -18,10 +18,10 @@ def _new_path(scn, p_lie):
     return s
 
 
-def test_update_and_reprojected_warm_start_match_host_mirror():
-    """Every step: builder (host build) vs mirror `prepare` — before the update (shifted warm start) and after it
-    (re-projected warm start incl. the fallback steps in which the previous solution is kept)."""
-    s = EmuSolver()
+def _replan_loop(s, update_fn, prepare_fn):
+    """Every step: builder vs mirror `prepare` — before the update (shifted warm start) and after it (re-projected warm
+    start incl. the fallback steps in which the previous solution is kept); `update_fn` / `prepare_fn` = the kernels
+    under test (host build or GPU), compared with the numpy mirror directly."""
     scn = scenarios.experiment1(n=10)
     mpc = batches.make_mpc(scn, s)
     rm = RobotModel()
@@ -46,7 +46,7 @@ def test_update_and_reprojected_warm_start_match_host_mirror():
                 T[k, :len(t)] = t
                 T[k, len(t):] = t[-1]
             tabs = T
-            st_u, sec_u, pid_u = emu.update(tabs, [0.0, mpc.ref_path.phi_max], [1], np.concatenate((p_lie, v, a_c, j_c)), st_old, [sec_old], path_id)
+            st_u, sec_u, pid_u = update_fn(tabs, [0.0, mpc.ref_path.phi_max], [1], np.concatenate((p_lie, v, a_c, j_c)), st_old, [sec_old], path_id)
             st_m, sec_m, _ = mpc.builder_state(q, dq, ddq, p_lie, v, x_phi_d, jerk)
             assert sec_u[0] == sec_m == 0 and pid_u[0] == 1
             keep = np.ones(76, bool); keep[50:53] = False            # (x_phi_d is the caller's)
@@ -54,7 +54,7 @@ def test_update_and_reprojected_warm_start_match_host_mirror():
             path_id = pid_u
         st, sector, prev = mpc.builder_state(q, dq, ddq, p_lie, v, x_phi_d, jerk)
         tab3 = tabs if isinstance(tabs, np.ndarray) else np.asarray(tabs)
-        x0e, pe, sece = emu.prepare(tab3, path_id, [sector], st, prev)
+        x0e, pe, sece = prepare_fn(tab3, path_id, [sector], st, prev)
         w0, params, aux = mpc.prepare(q, dq, ddq, p_lie, v, x_phi_d, jerk)
         assert sece[0] == mpc.ref_path.sector
         assert (np.abs(pe[0] - params) / np.maximum(1.0, np.abs(params))).max() < 1e-12
@@ -72,6 +72,33 @@ def test_update_and_reprojected_warm_start_match_host_mirror():
         q, dq, ddq, p_lie, v, a_c, j_c = integrate_joint(rm, jm, q, dq, ddq, mpc.dt)
         jerk = traj['dddq'][:, 0].copy()
     assert "project" in cases and len(errs) >= 20       # at least 8 steps after the update were compared
+
+
+def test_update_and_reprojected_warm_start_match_host_mirror():
+    _replan_loop(EmuSolver(), emu.update, emu.prepare)
+
+
+@pytest.mark.gpu
+def test_gpu_update_and_reprojection_match_host_mirror():
+    """k_update and k_prepare (re-projected warm start) on the GPU against the numpy mirror's `update` / `prepare` directly
+    (not via the host build of the same source), along a closed loop with a replanning event."""
+    import torch
+    from boundmpc_b200.ocp import default_solver
+    s = default_solver()
+    dev = torch.device("cuda")
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a), dt)).to(dev)
+
+    def update_fn(tabs, phimax, new_path, cart, state, sector, path_id):
+        t = dict(tables=T(tabs, np.float64), phimax=T(phimax, np.float64), new_path=T(new_path, np.int32), cart=T(np.atleast_2d(cart), np.float64),
+                 state=T(np.atleast_2d(state), np.float64), sector=T(sector, np.int32), path_id=T(path_id, np.int32))
+        s.update_batch(t["tables"], t["phimax"], t["new_path"], t["cart"], t["state"], t["sector"], t["path_id"])
+        return t["state"].cpu().numpy(), t["sector"].cpu().numpy(), t["path_id"].cpu().numpy()
+
+    def prepare_fn(tabs, path_id, sector, st, prev):
+        r = s.prepare_batch(np.asarray(tabs), np.asarray(path_id, np.int32), np.asarray(sector, np.int32), np.atleast_2d(st), np.atleast_2d(prev))
+        return r["x0"], r["p"], r["sector"]
+
+    _replan_loop(s, update_fn, prepare_fn)
 
 
 @pytest.mark.gpu
