@@ -50,7 +50,7 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 // long solves; two lists (hard / normal) still 8 % behind the ordinary 15-iteration ones picked up last.  Results do not
 // depend on where an instance is parked.
 constexpr int SCHED_LISTS = 4;
-constexpr int SAVE_FILT = 128, SAVE_SCAL = 16;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4])
+constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls)
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
 enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
 enum { DONE = 0, PARKED = 1 };                                   // its return value: DONE or PARKED + priority list
@@ -120,7 +120,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   // progress monitor of the barrier update: optimality errors of the last accepted iterates (CTA-uniform registers),
   // sum of the fraction-to-the-boundary step limits so far (scheduling hint), largest barrier parameter used
   double refs[4] = {0.0, 0.0, 0.0, 0.0}, apr_sum = 0.0, mu_top = C.mu_init;
-  int nref = 0;
+  int nref = 0, stalls = 0;
   if (mode == RUN_RESUME) {
     // ---- restore the parked iterate
     build_wp0(cx, C, p, W.wp0);
@@ -138,6 +138,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     if (cx.tid == 0) S.flag[1] = (int)BMPC_LDCG(q + 8);
     nref = (int)BMPC_LDCG(q + 9); apr_sum = BMPC_LDCG(q + 10); mu_top = BMPC_LDCG(q + 11);
     for (int r = 0; r < 4; r++) refs[r] = BMPC_LDCG(q + 12 + r);
+    stalls = (int)BMPC_LDCG(q + 16);
     BMPC_SYNC();
   } else {
   // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)
@@ -191,6 +192,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         q[5] = have_theta0 ? 1.0 : 0.0; q[6] = (double)it; q[7] = (double)ls_fail; q[8] = (double)S.flag[1];
         q[9] = (double)nref; q[10] = apr_sum; q[11] = mu_top;
         for (int r = 0; r < 4; r++) q[12 + r] = refs[r];
+        q[16] = (double)stalls;
       }
       BMPC_SYNC();
       // priority list (see SCHED_LISTS).  "hard": on the bench workload these tests flag 6 % of the batch and every
@@ -315,7 +317,13 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         mu_top = fmax(mu_top, mu);
         mu_changed = true;
         nref = 0;
-      }
+      } else if (C.stall_stop > 0 && ++stalls >= C.stall_stop) {
+        // re-centring exhausted (mu at its cap) and, for the stall_stop-th time, no progress: the multipliers of rows that
+        // cannot be satisfied keep growing -- locally infeasible (Ipopt ends its restoration phase at a stationary point of
+        // the constraint violation, "Converged to a point of local infeasibility").  Certified independently for the
+        // config-4 fixtures (tests/test_config4.py); no converging instance of the bench workload gets here.
+        status = ST_DIVERGING; break;
+      } else nref = 0;
     }
     if (mu_changed) { if (cx.tid == 0) S.flag[1] = 0; BMPC_SYNC(); }
     if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * fmax(1.0, th_cur); theta_min = 1e-4 * fmax(1.0, th_cur); }

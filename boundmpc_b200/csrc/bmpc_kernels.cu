@@ -488,12 +488,13 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     for (int v = 0; v < kNumVariants; v++)
       if (kVariants[v].threads == 384 && kVariants[v].minb == 1) h->variant_lat = v;
   e = cudaSuccess;
-  // horizons above VEC_NMAX: the iterate (N x 192 doubles) goes behind the struct when two CTAs per SM still fit
-  // (BMPC_VEC_GLOBAL=1: leave it in the workspace, three CTAs per SM -- the trade-off is measured in DESIGN.md)
+  // horizons above VEC_NMAX: the iterate (N x 192 doubles) stays in the workspace (L2) and three CTAs per SM run; with
+  // BMPC_VEC_SMEM=1 it goes behind the struct (two CTAs per SM).  Measured on config 4 (N = 20, 8,192 instances): 9,977
+  // solves/s from the workspace against 9,031 on chip -- the third resident CTA is worth more than the L2 round trips.
   h->smem_solve = sizeof(Smem);
   {
     const size_t ext = (size_t)h->C.N * (3 * NX + NE + 2 * ND) * sizeof(double);
-    if (h->C.N > VEC_NMAX && !getenv("BMPC_VEC_GLOBAL") && 2 * (sizeof(Smem) + ext + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) h->smem_solve += ext;
+    if (h->C.N > VEC_NMAX && getenv("BMPC_VEC_SMEM") && 2 * (sizeof(Smem) + ext + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) h->smem_solve += ext;
   }
   if (h->variant_lat >= 0) e = cudaFuncSetAttribute(kVariants[h->variant_lat].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solve);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kVariants[h->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solve);

@@ -309,6 +309,7 @@ struct Opts {
   int red_iters = 3;          // progress test: no improvement on any of the last red_iters accepted iterates ...
   double boost_fac = 10, boost_cap = 1.0;   // ... -> mu <- min(cap, fac * mu)
   int max_soc = 1;            // second-order corrections per iteration
+  int stall_stop = 3;         // third time without progress with mu at its cap: stop as locally infeasible
 };
 
 struct Ipm {
@@ -611,7 +612,7 @@ struct Ipm {
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
     int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
-    int n_soc = 0;
+    int n_soc = 0, stalls = 0;
     std::vector<double> refs;
     for (;; it++) {
       pack_lam();
@@ -646,7 +647,12 @@ struct Ipm {
             mu = std::min(o.boost_cap, o.boost_fac * mu);
             filter.clear(); refs.clear();
             if (o.verbose) printf("      no progress: mu -> %.3e\n", mu);
-          }
+          } else if (o.stall_stop && ++stalls >= o.stall_stop) {
+            // re-centring exhausted (mu at its cap) and still no progress: the multipliers of rows that cannot be satisfied
+            // keep growing -- the instance is locally infeasible (Ipopt would end its restoration phase at a stationary point
+            // of the constraint violation: "Converged to a point of local infeasibility")
+            status = 5; break;
+          } else refs.clear();
         }
       }
       double th_cur = theta(E.g.data(), E.d.data(), s);
@@ -946,6 +952,7 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
   }
   if (opts && opts[5] >= 0) o.mu_strategy = (int)opts[5];
   if (opts && opts[6] >= 0) o.max_soc = (int)opts[6];
+  if (const char* e = getenv("ORC_STALL")) o.stall_stop = atoi(e);
   Ipm ipm(P, p, o);
   ipm.trace = g_trace; ipm.trace_cap = g_trace_cap;
   int it = 0;
