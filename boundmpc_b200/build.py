@@ -13,16 +13,19 @@ import glob
 def _headers():
     """Everything the translation unit can include, plus this file (the flags are part of the build)."""
     return (sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")))
-            + [os.path.join(HERE, "..", "include", "boundmpc_b200.h"), os.path.abspath(__file__)])
+            + [os.path.join(HERE, "..", "include", "boundmpc_b200.h")])
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared", "-diag-suppress", "128"]
 
 
+def _digest():
+    from ._buildutil import content_hash
+    return content_hash([os.path.join(CSRC, s) for s in SOURCES] + _headers(), " ".join(NVCC_FLAGS))
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, s) for s in SOURCES] + _headers())
+    from ._buildutil import is_current
+    return not is_current(LIB, _digest())
 
 
 TIMING_LIB = os.path.join(HERE, "libboundmpc_b200_timing.so")   # development build with per-phase cycle counters
@@ -37,15 +40,23 @@ def build(force=False, verbose=False, timing=False, defines=(), out=None):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
         return target
-    if not force and not needs_build():
+    from ._buildutil import build_lock, is_current, mark_current
+    digest = _digest()
+    if not force and is_current(LIB, digest):
         return LIB
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with build_lock(LIB):
+        if not force and is_current(LIB, digest):          # another process built it while this one waited
+            return LIB
+        nvcc = os.environ.get("NVCC", "nvcc")
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB)
+        mark_current(LIB, digest)
+        if verbose:
+            print(r.stderr)
     return LIB
 
 

@@ -414,6 +414,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
 struct bmpc_handle {
   Config C;
   int device, threads, sms, ctas_per_sm, variant;
+  size_t l2_window_max, l2_persist_bytes;   // L2 access-policy window for the workspace (0: off)
   size_t smem_solve;   // dynamic shared memory of k_solve: sizeof(Smem) [+ the iterate of horizons above VEC_NMAX]
   int single_pass, no_zero_copy;   // development switches, read from the environment once in bmpc_create
   int variant_lat;     // launch shape for batches of at most one instance per SM (-1: none): more threads per instance
@@ -507,6 +508,16 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->ctas_per_sm = want_c < occ ? want_c : occ;
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
   h->launches = 0;
+  // persisting-L2 carve-out for the workspace window (see solve_batch_impl); BMPC_NO_L2_WINDOW=1 switches it off
+  h->l2_window_max = h->l2_persist_bytes = 0;
+  if (!getenv("BMPC_NO_L2_WINDOW") && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+    size_t want = (size_t)h->sms * h->ctas_per_sm * h->ws_stride * sizeof(double);
+    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+      h->l2_persist_bytes = want;
+      h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    } else cudaGetLastError();
+  }
   h->single_pass = getenv("BMPC_SINGLE_PASS") != nullptr;
   h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
   if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
@@ -622,7 +633,27 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
   }
   BatchIO io{x0, p, x, g, lam_g, lam_x, f, kkt_err, iters, status, x0_src, p_src};
   const int v = (h->variant_lat >= 0 && batch <= h->sms) ? h->variant_lat : h->variant;
-  kVariants[v].fn<<<grid, kVariants[v].threads, h->smem_solve, st>>>(h->C, batch, io, ws, h->ws_stride, M, h->smem_solve > sizeof(Smem) ? 1 : 0);
+  // The per-CTA workspace slices (150 KB each, 67 MB for a full grid) are the only data the kernel re-reads; inputs and
+  // results stream through once.  An access-policy window marks the slices as persisting in L2 and everything else as
+  // streaming, so the 176 MB of inputs / outputs of a large batch no longer evict (and write back) workspace lines.
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(kVariants[v].threads); lc.dynamicSmemBytes = h->smem_solve; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  int nat = 0;
+  if (h->l2_window_max > 0 && batch > grid) {
+    size_t wbytes = (size_t)grid * h->ws_stride * sizeof(double);
+    if (wbytes > h->l2_window_max) wbytes = h->l2_window_max;
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = ws;
+    at[0].val.accessPolicyWindow.num_bytes = wbytes;
+    at[0].val.accessPolicyWindow.hitRatio = h->l2_persist_bytes >= wbytes ? 1.0f : (float)h->l2_persist_bytes / (float)wbytes;
+    at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    nat = 1;
+  }
+  lc.attrs = at; lc.numAttrs = nat;
+  const int vec_ext = h->smem_solve > sizeof(Smem) ? 1 : 0;
+  CU(cudaLaunchKernelEx(&lc, kVariants[v].fn, h->C, batch, io, ws, h->ws_stride, M, vec_ext));
   CU(cudaGetLastError());
   h->launches += 1;
   return BMPC_OK;

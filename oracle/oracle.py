@@ -12,9 +12,26 @@ _ip = ctypes.POINTER(ctypes.c_int)
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("boundmpc_oracle.cpp", "ocp_model.hpp", "ad.hpp")]
-    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    """gcc build of the oracle (content hash, lock, atomic replace: see boundmpc_b200/_buildutil.py)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from boundmpc_b200._buildutil import content_hash, is_current, mark_current, build_lock
+    srcs = [os.path.join(_HERE, f) for f in ("boundmpc_oracle.cpp", "ocp_model.hpp", "ad.hpp", "Makefile")]
+    # (-march=native: the library is specific to the host CPU, so its feature flags are part of the key and a box with another
+    # CPU rebuilds instead of loading code it cannot execute)
+    try:
+        cpu = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except (OSError, StopIteration):
+        cpu = ""
+    digest = content_hash(srcs, cpu)
+    if not force and is_current(_LIB, digest):
+        return _LIB
+    with build_lock(_LIB):
+        if force or not is_current(_LIB, digest):
+            tmp = f"libboundmpc_oracle.tmp.{os.getpid()}.so"
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", f"OUT={tmp}"])
+            os.replace(os.path.join(_HERE, tmp), _LIB)
+            mark_current(_LIB, digest)
     return _LIB
 
 

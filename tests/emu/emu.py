@@ -33,10 +33,19 @@ def make_cfg(N=10, S=4, dt=0.1, tol=1e-9, max_iter=500):
 
 
 def build(force=False):
+    from boundmpc_b200._buildutil import content_hash, is_current, mark_current, build_lock
     src = [os.path.join(_HERE, "bmpc_emu.cpp")] + [os.path.join(_ROOT, "boundmpc_b200", "csrc", f) for f in
            ("bmpc_common.h", "bmpc_model.cuh", "bmpc_riccati.cuh", "bmpc_ipm.cuh", "bmpc_eval.cuh", "bmpc_host.h", "bmpc_prepare.cuh", "bmpc_post.cuh")]
-    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB, src[0]])
+    src.append(os.path.join(_ROOT, "include", "boundmpc_b200.h"))
+    digest = content_hash(src)
+    if not force and is_current(_LIB, digest):
+        return _LIB
+    with build_lock(_LIB):
+        if force or not is_current(_LIB, digest):
+            tmp = f"{_LIB}.tmp.{os.getpid()}"
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", tmp, src[0]])
+            os.replace(tmp, _LIB)
+            mark_current(_LIB, digest)
     return _LIB
 
 
