@@ -238,6 +238,7 @@ struct Config {
   double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
   double boost_fac, boost_cap;   // re-centring of a crawling iteration (bmpc_ipm.cuh): mu <- min(cap, fac * mu)
   int stall_stop;                // stop as locally infeasible at the stall_stop-th failed progress test with mu at its cap (0: never)
+  int soc_budget;                // corrections rejected in a row after which none is tried any more in a solve
   int max_soc;                   // second-order corrections per iteration (0 or 1)
   int slice_iters;               // iterations of pass A of the two-pass scheduling (bmpc_ipm.cuh)
   int red_iters;                 // ... when the optimality error has not improved on any of the last red_iters iterates (<= 4)

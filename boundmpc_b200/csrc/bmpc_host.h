@@ -47,7 +47,7 @@ inline int make_config(const bmpc_config& in, Config& C) {
   C.slice_iters = 6;
   // One second-order correction per iteration (Ipopt: max_soc = 4; on the bench workload a second correction is never
   // accepted when the first is not): 0.9 % extra KKT solves, 7 % fewer iterations along the experiment1 closed loop.
-  C.max_soc = 1;
+  C.max_soc = 1; C.soc_budget = 2;
   C.gamma_theta = 1e-5; C.gamma_phi = 1e-5; C.eta_phi = 1e-8; C.s_phi = 2.3; C.s_theta = 1.1;
   const double h = in.dt;
   C.a_dq = h; C.a_ddq = h * h / 2; C.a_um = h * h * h / 8; C.a_u = h * h * h / 24;

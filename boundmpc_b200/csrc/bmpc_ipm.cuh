@@ -50,7 +50,7 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 // long solves; two lists (hard / normal) still 8 % behind the ordinary 15-iteration ones picked up last.  Results do not
 // depend on where an instance is parked.
 constexpr int SCHED_LISTS = 4;
-constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls)
+constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls, soc_fails)
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
 enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
 enum { DONE = 0, PARKED = 1 };                                   // its return value: DONE or PARKED + priority list
@@ -120,7 +120,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   // progress monitor of the barrier update: optimality errors of the last accepted iterates (CTA-uniform registers),
   // sum of the fraction-to-the-boundary step limits so far (scheduling hint), largest barrier parameter used
   double refs[4] = {0.0, 0.0, 0.0, 0.0}, apr_sum = 0.0, mu_top = C.mu_init;
-  int nref = 0, stalls = 0;
+  int nref = 0, stalls = 0, soc_fails = 0;
   if (mode == RUN_RESUME) {
     // ---- restore the parked iterate
     build_wp0(cx, C, p, W.wp0);
@@ -138,7 +138,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     if (cx.tid == 0) S.flag[1] = (int)BMPC_LDCG(q + 8);
     nref = (int)BMPC_LDCG(q + 9); apr_sum = BMPC_LDCG(q + 10); mu_top = BMPC_LDCG(q + 11);
     for (int r = 0; r < 4; r++) refs[r] = BMPC_LDCG(q + 12 + r);
-    stalls = (int)BMPC_LDCG(q + 16);
+    stalls = (int)BMPC_LDCG(q + 16); soc_fails = (int)BMPC_LDCG(q + 17);
     BMPC_SYNC();
   } else {
   // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)
@@ -192,7 +192,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         q[5] = have_theta0 ? 1.0 : 0.0; q[6] = (double)it; q[7] = (double)ls_fail; q[8] = (double)S.flag[1];
         q[9] = (double)nref; q[10] = apr_sum; q[11] = mu_top;
         for (int r = 0; r < 4; r++) q[12 + r] = refs[r];
-        q[16] = (double)stalls;
+        q[16] = (double)stalls; q[17] = (double)soc_fails;
       }
       BMPC_SYNC();
       // priority list (see SCHED_LISTS).  "hard": on the bench workload these tests flag 6 % of the batch and every
@@ -359,7 +359,9 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     const bool flat = th_cur <= 1e-10 && fabs(dphi) <= 1e-10 * fmax(1.0, fabs(phi_cur));
     // soc: 0 = regular trials, 1 = the trial of the corrected step is being tested (alpha = its fraction-to-the-boundary limit,
     // acceptance still measured with the length a_sw = apr of the rejected full step), 2 = correction used up
-    int soc = C.max_soc > 0 ? 0 : 2;
+    // (after soc_budget corrections rejected in a row no more are tried in this solve: an infeasible crawl rejects every one
+    // of them, at two extra sweeps each)
+    int soc = (C.max_soc > 0 && soc_fails < C.soc_budget) ? 0 : 2;
     for (int ls = 0; ls < 40;) {
       PAR_FOR(i, n) W.xt[i] = W.x[i] + alpha * W.dx[i];
       PAR_FOR(i, nd) W.st[i] = W.s[i] + alpha * W.ds[i];
@@ -406,7 +408,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
           }
         }
       }
-      if (acc) { accepted = true; ftype = ft; break; }
+      if (acc) { accepted = true; ftype = ft; if (soc == 1) soc_fails = 0; break; }
       if (soc == 0 && ls == 0 && fin && th_t >= th_cur) {
         // ---- second-order correction: the full step has not reduced the constraint violation (the Maratos effect of the
         // kinematic rows).  Re-solve with the residuals c_soc = alpha c(x_k) + c(x_k + alpha dx) and this iteration's
@@ -438,6 +440,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       if (soc == 1) {
         // the corrected step was rejected (or could not be computed): back to the Newton step of this iteration
         soc = 2;
+        soc_fails++;
         eval_values(cx, C, W, p, W.x, W.c, W.d);
         kkt_prepare(cx, C, W, mu);
         kkt_solve(cx, C, W, p, S, dwreg);

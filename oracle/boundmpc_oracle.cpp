@@ -309,6 +309,7 @@ struct Opts {
   int red_iters = 3;          // progress test: no improvement on any of the last red_iters accepted iterates ...
   double boost_fac = 10, boost_cap = 1.0;   // ... -> mu <- min(cap, fac * mu)
   int max_soc = 1;            // second-order corrections per iteration
+  int soc_budget = 2;         // ... until this many corrections in a row have been rejected
   int stall_stop = 3;         // third time without progress with mu at its cap: stop as locally infeasible
 };
 
@@ -612,7 +613,7 @@ struct Ipm {
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
     int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
-    int n_soc = 0, stalls = 0;
+    int n_soc = 0, stalls = 0, soc_fails = 0;
     std::vector<double> refs;
     for (;; it++) {
       pack_lam();
@@ -753,7 +754,7 @@ struct Ipm {
         th_t = theta(gt.data(), dt_.data(), st);
         ph_t = barrier_phi(ft, xt, st);
         if (acceptable(th_t, ph_t, alpha, ftype)) { accepted = true; break; }
-        if (ls == 0 && o.max_soc > 0 && std::isfinite(th_t) && th_t >= th_cur) {
+        if (ls == 0 && o.max_soc > 0 && soc_fails < o.soc_budget && std::isfinite(th_t) && th_t >= th_cur) {
           // ---- second-order correction (Waechter & Biegler 2006, Sec. 2.4; Ipopt max_soc = 4, kappa_soc = 0.99): the
           // rejected full step has not reduced the constraint violation; re-solve with the residuals
           // c_soc = alpha c(x_k) + c(x_k + alpha dx) and the factorisation of this iteration
@@ -790,7 +791,8 @@ struct Ipm {
               for (int i = 0; i < ND; i++) cs_d[ND * k + i] = a_soc * cs_d[ND * k + i] + dt_[ND * k + i] + st[ND * k + i];
             }
           }
-          if (soc_ok) { accepted = true; n_soc++; g_soc_accepted++; break; }
+          if (soc_ok) { accepted = true; n_soc++; g_soc_accepted++; soc_fails = 0; break; }
+          soc_fails++;      // (soc_budget corrections rejected in a row: no more attempts in this solve)
           dx = dx0; ds = ds0; ynew = y0; dzs = dzs0; dzL = dzL0; dzU = dzU0;
         }
       }
@@ -953,6 +955,7 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
   if (opts && opts[5] >= 0) o.mu_strategy = (int)opts[5];
   if (opts && opts[6] >= 0) o.max_soc = (int)opts[6];
   if (const char* e = getenv("ORC_STALL")) o.stall_stop = atoi(e);
+  if (const char* e = getenv("ORC_SOCB")) o.soc_budget = atoi(e);
   Ipm ipm(P, p, o);
   ipm.trace = g_trace; ipm.trace_cap = g_trace_cap;
   int it = 0;
