@@ -489,7 +489,7 @@ def main():
         post["hbm"].update(peak=hbm_peak, frac=post["hbm"]["achieved"] / hbm_peak)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get("k_solve_dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     line = {"metric": METRIC, "value": total * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": max(1, world),

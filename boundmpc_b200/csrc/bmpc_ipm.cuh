@@ -176,7 +176,13 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   const double nzcnt = (double)N * (ND + nbnd);
 
   for (;; it++) {
-    if (mode == RUN_SLICE && it == C.slice_iters) {
+    // "hard" (see SCHED_LISTS): on the bench workload these tests flag 6 % of the batch and every instance with more than
+    // 22 iterations to go.  With C.hard_continue a hard instance is not parked at all but goes on at once (measured: no gain
+    // over resuming it first in pass B, a solve picked up late in pass A is the tail either way; off by default).
+    const bool slice_end = mode == RUN_SLICE && it == C.slice_iters;
+    const bool hard = slice_end && (kkt_final > e0_first || mu_top > C.mu_init || apr_sum < 0.3 * it);
+    if (slice_end && hard && C.hard_continue) mode = RUN_FULL;
+    else if (slice_end) {
       // ---- park the iterate (every quantity the loop carries; everything else is recomputed by eval_full)
       double* q = save;
       PAR_FOR(i, n) { q[i] = W.x[i]; q[n + i] = W.zL[i]; q[2 * n + i] = W.zU[i]; }
@@ -195,9 +201,8 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         q[16] = (double)stalls; q[17] = (double)soc_fails;
       }
       BMPC_SYNC();
-      // priority list (see SCHED_LISTS).  "hard": on the bench workload these tests flag 6 % of the batch and every
-      // instance with more than 22 iterations to go
-      if (kkt_final > e0_first || mu_top > C.mu_init || apr_sum < 0.3 * it) return PARKED + 0;
+      // priority list (see SCHED_LISTS)
+      if (hard) return PARKED + 0;
       return PARKED + (kkt_final >= 0.1 ? 1 : (kkt_final >= 1e-4 ? 2 : 3));
     }
     eval_full(cx, C, W, p, W.x);

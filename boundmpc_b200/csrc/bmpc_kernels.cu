@@ -411,6 +411,19 @@ static int fail(int code, const char* fmt, const char* a = "") {
     if (e_ != cudaSuccess) return fail(BMPC_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
   } while (0)
 
+// Entry points run on the handle's device and put the caller's current device back when they return (a handle created for
+// another device than the caller's current one must not change what torch / the caller sees as current).
+struct DevGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    if (prev == dev) { prev = -1; ok = true; return; }
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct bmpc_handle {
   Config C;
   int device, threads, sms, ctas_per_sm, variant;
@@ -508,9 +521,11 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->ctas_per_sm = want_c < occ ? want_c : occ;
   h->ws_stride = align_up(work_doubles(h->C.N), 32);
   h->launches = 0;
-  // persisting-L2 carve-out for the workspace window (see solve_batch_impl); BMPC_NO_L2_WINDOW=1 switches it off
+  // persisting-L2 carve-out for the workspace window (see solve_batch_impl): opt-in with BMPC_L2_WINDOW=1.  Measured on the
+  // bench shard: 54.9 vs 55.6 ms in an interleaved A/B, 55.4 vs 55.0 ms under ncu, and MORE DRAM write-back (17.1 vs 12.3 GB
+  // per launch: the 67 MB of slices exceed the persisting carve-out and everything else is demoted to streaming).
   h->l2_window_max = h->l2_persist_bytes = 0;
-  if (!getenv("BMPC_NO_L2_WINDOW") && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+  if (getenv("BMPC_L2_WINDOW") && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
     size_t want = (size_t)h->sms * h->ctas_per_sm * h->ws_stride * sizeof(double);
     if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
@@ -522,6 +537,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
   if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
   if (const char* e_ = getenv("BMPC_MAX_SOC")) h->C.max_soc = atoi(e_) > 0 ? 1 : 0;
+  if (const char* e_ = getenv("BMPC_HARD_CONTINUE")) h->C.hard_continue = atoi(e_) > 0 ? 1 : 0;
   h->dbuf = nullptr; h->dbuf_bytes = 0;
   h->pin = nullptr; h->pin_bytes = 0;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -574,7 +590,8 @@ int bmpc_launch_shape(const bmpc_handle* h, int32_t* threads, int32_t* ctas_per_
 
 int bmpc_fp64_peak(bmpc_handle* h, int32_t kind, double* flops_per_s) {
   if (!h || !flops_per_s || kind < 0 || kind > 1) return fail(BMPC_E_INVALID, "bmpc_fp64_peak: invalid argument");
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   int rc = ensure_dbuf(h, 256);
   if (rc) return rc;
   const int iters = 4096, grid = h->sms * 8, threads = 256;
@@ -615,7 +632,8 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
   if (batch < 0 || !x0 || !p || !x || !g || !lam_g || !lam_x || !f || !iters || !status || !kkt_err || !workspace)
     return fail(BMPC_E_INVALID, "bmpc_solve_batch: null buffer");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int grid = grid_for(h, batch);
   // workspace: [queue 256 B][per-CTA slices][parked lists 2 x batch int][parked iterates batch x save_stride]
@@ -672,7 +690,8 @@ int bmpc_solve_batch_host(bmpc_handle* h, int32_t batch, const double* x0, const
   if (!h) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null handle");
   if (batch < 0 || !x0 || !p || !x || !iters || !status) return fail(BMPC_E_INVALID, "bmpc_solve_batch_host: null buffer");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   // Small batches in pageable memory (the single MPC step of a Python / ROS caller): ten small copies around the launch
   // cost more than the transfers themselves.  They are staged through a page-locked area of the handle, which the
   // kernel reads and writes itself (see below): two host memcpys and one launch.
@@ -757,7 +776,8 @@ int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables,
     return fail(BMPC_E_INVALID, "bmpc_prepare_batch: invalid argument");
   if (h->C.S > PREP_SMAX) return fail(BMPC_E_INVALID, "bmpc_prepare_batch: nr_segs above the builder's limit");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   PrepIO io{path_tables, path_rows, path_id, sector, state, prev_x, x0, p};
   k_prepare<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
@@ -768,10 +788,11 @@ int bmpc_prepare_batch(bmpc_handle* h, int32_t batch, const double* path_tables,
 int bmpc_prepare_batch_host(bmpc_handle* h, int32_t batch, const double* path_tables, int32_t n_paths, int32_t path_rows,
                             const int32_t* path_id, int32_t* sector, const double* state, const double* prev_x, double* x0, double* p) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_prepare_batch_host: null handle");
-  if (batch < 0 || n_paths < 1 || !path_tables || !path_id || !sector || !state || !prev_x || !x0 || !p)
+  if (batch < 0 || n_paths < 1 || path_rows < h->C.S || !path_tables || !path_id || !sector || !state || !prev_x || !x0 || !p)
     return fail(BMPC_E_INVALID, "bmpc_prepare_batch_host: invalid argument");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   const size_t B = batch, n = h->C.n, np = h->C.np, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
@@ -803,7 +824,8 @@ int bmpc_post_batch(bmpc_handle* h, int32_t batch, const double* path_tables, in
   if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !w || !traj || !state_out)
     return fail(BMPC_E_INVALID, "bmpc_post_batch: invalid argument");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out, nullptr, nullptr, nullptr};
   k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
@@ -817,7 +839,8 @@ int bmpc_update_batch(bmpc_handle* h, int32_t batch, const double* path_tables, 
   if (batch < 0 || n_paths < 1 || path_rows < 1 || !path_tables || !path_phi_max || !new_path || !cart || !state || !sector || !path_id)
     return fail(BMPC_E_INVALID, "bmpc_update_batch: invalid argument");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   UpdateIO io{path_tables, path_rows, path_phi_max, new_path, cart, state, sector, path_id};
   k_update<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(batch, io);
   CU(cudaGetLastError());
@@ -833,7 +856,8 @@ int bmpc_post_log_batch(bmpc_handle* h, int32_t batch, const double* path_tables
     return fail(BMPC_E_INVALID, "bmpc_post_log_batch: invalid argument");
   if (h->C.S < 3) return fail(BMPC_E_INVALID, "bmpc_post_log_batch: the rotation reference of the logging branch needs nr_segs >= 3");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   PostIO io{path_tables, path_rows, path_id, sector, state, w, error_count, traj, state_out, p, ref, err};
   k_post<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
   CU(cudaGetLastError());
@@ -851,7 +875,8 @@ static int finish_impl(bmpc_handle* h, int32_t batch, const double* path_tables,
     return fail(BMPC_E_INVALID, "bmpc_finish_batch: invalid argument");
   if (ref && (h->C.S < 3 || path_rows < 3 || !p || !err)) return fail(BMPC_E_INVALID, "bmpc_finish_batch: the logging branch needs p, err and nr_segs >= 3");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   FinishIO io{{path_tables, path_rows, path_id, sector, state, x, error_count, traj, state_out, ref ? p : nullptr, ref, ref ? err : nullptr}, g, status,
               prev_x, error_count, advance};
   k_finish<<<(batch + PREP_THREADS - 1) / PREP_THREADS, PREP_THREADS, 0, (cudaStream_t)cuda_stream>>>(h->C, batch, io);
@@ -878,7 +903,8 @@ int bmpc_mpc_step_batch_host(bmpc_handle* h, int32_t batch, const double* path_t
     return fail(BMPC_E_INVALID, "bmpc_mpc_step_batch_host: invalid argument");
   if (h->C.S > PREP_SMAX) return fail(BMPC_E_INVALID, "bmpc_mpc_step_batch_host: nr_segs above the builder's limit");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np, N = h->C.N, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
   size_t wsb = 0;
   bmpc_workspace_bytes(h, batch, &wsb);
@@ -936,10 +962,11 @@ int bmpc_post_batch_host(bmpc_handle* h, int32_t batch, const double* path_table
                          const int32_t* sector, const double* state, const double* w, const int32_t* error_count, double* traj,
                          double* state_out) {
   if (!h) return fail(BMPC_E_INVALID, "bmpc_post_batch_host: null handle");
-  if (batch < 0 || n_paths < 1 || !path_tables || !path_id || !sector || !state || !w || !traj || !state_out)
+  if (batch < 0 || n_paths < 1 || path_rows < 2 || !path_tables || !path_id || !sector || !state || !w || !traj || !state_out)
     return fail(BMPC_E_INVALID, "bmpc_post_batch_host: invalid argument");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   const size_t B = batch, n = h->C.n, tr = (size_t)h->C.N * TR_ROW, tb = (size_t)n_paths * path_rows * PT_ROW * 8;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
@@ -969,7 +996,8 @@ int bmpc_eval_batch_host(bmpc_handle* h, int32_t batch, const double* x, const d
   if (!h) return fail(BMPC_E_INVALID, "bmpc_eval_batch_host: null handle");
   if (batch < 0 || !x || !p) return fail(BMPC_E_INVALID, "bmpc_eval_batch_host: null buffer");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   const size_t B = batch, n = h->C.n, m = h->C.m, np = h->C.np, nl = (size_t)(NE + ND) * h->C.N, ndd = (size_t)ND * h->C.N;
   const int grid = grid_for(h, batch);
   size_t off = 0;
@@ -1004,7 +1032,8 @@ int bmpc_kkt_step_batch_host(bmpc_handle* h, int32_t batch, const double* v, con
   if (!h) return fail(BMPC_E_INVALID, "bmpc_kkt_step_batch_host: null handle");
   if (batch < 0 || !v || !p || !mu || !delta_w || !dx || !ynew || !ok) return fail(BMPC_E_INVALID, "bmpc_kkt_step_batch_host: null buffer");
   if (batch == 0) return BMPC_OK;
-  CU(cudaSetDevice(h->device));
+  DevGuard dg_(h->device);
+  if (!dg_.ok) return fail(BMPC_E_CUDA, "cudaSetDevice failed");
   const size_t B = batch, n = h->C.n, ne = (size_t)NE * h->C.N, nv = 3 * n + ne + 2 * (size_t)ND * h->C.N, np = h->C.np;
   const int grid = grid_for(h, batch);
   size_t off = 0;

@@ -42,6 +42,7 @@ int emu_solve_sliced(const bmpc_config* cfg, int batch, const double* x0, const 
                      double* lam_x, double* f, int32_t* iters, int32_t* status, double* kkt, int32_t* hard) {
   Config C;
   if (make_config(*cfg, C)) return -1;
+  C.hard_continue = 0;          // park every instance, the hard ones too: the save / restore path is what this entry tests
   std::vector<double> ws(work_doubles(C.N));
   const size_t stride = save_doubles(C.N);
   std::vector<double> save(stride * (size_t)batch);
