@@ -237,6 +237,7 @@ struct Config {
   double mu_init, bound_push;
   double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
   double boost_fac, boost_cap;   // re-centring of a crawling iteration (bmpc_ipm.cuh): mu <- min(cap, fac * mu)
+  int boost_budget;              // re-centrings per solve before it is stopped as locally infeasible
   int stall_stop;                // stop as locally infeasible at the stall_stop-th failed progress test with mu at its cap (0: never)
   int soc_budget;                // corrections rejected in a row after which none is tried any more in a solve
   int max_soc;                   // second-order corrections per iteration (0 or 1)

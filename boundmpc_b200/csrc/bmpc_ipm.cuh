@@ -50,7 +50,7 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 // long solves; two lists (hard / normal) still 8 % behind the ordinary 15-iteration ones picked up last.  Results do not
 // depend on where an instance is parked.
 constexpr int SCHED_LISTS = 4;
-constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls, soc_fails)
+constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls, soc_fails, boosts)
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
 enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
 enum { DONE = 0, PARKED = 1 };                                   // its return value: DONE or PARKED + priority list
@@ -120,7 +120,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   // progress monitor of the barrier update: optimality errors of the last accepted iterates (CTA-uniform registers),
   // sum of the fraction-to-the-boundary step limits so far (scheduling hint), largest barrier parameter used
   double refs[4] = {0.0, 0.0, 0.0, 0.0}, apr_sum = 0.0, mu_top = C.mu_init;
-  int nref = 0, stalls = 0, soc_fails = 0;
+  int nref = 0, stalls = 0, soc_fails = 0, boosts = 0;
   if (mode == RUN_RESUME) {
     // ---- restore the parked iterate
     build_wp0(cx, C, p, W.wp0);
@@ -138,7 +138,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
     if (cx.tid == 0) S.flag[1] = (int)BMPC_LDCG(q + 8);
     nref = (int)BMPC_LDCG(q + 9); apr_sum = BMPC_LDCG(q + 10); mu_top = BMPC_LDCG(q + 11);
     for (int r = 0; r < 4; r++) refs[r] = BMPC_LDCG(q + 12 + r);
-    stalls = (int)BMPC_LDCG(q + 16); soc_fails = (int)BMPC_LDCG(q + 17);
+    stalls = (int)BMPC_LDCG(q + 16); soc_fails = (int)BMPC_LDCG(q + 17); boosts = (int)BMPC_LDCG(q + 18);
     BMPC_SYNC();
   } else {
   // ---- initial point: push into the bounds (Ipopt warm_start_bound_push), slacks from d(x0)
@@ -198,7 +198,7 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         q[5] = have_theta0 ? 1.0 : 0.0; q[6] = (double)it; q[7] = (double)ls_fail; q[8] = (double)S.flag[1];
         q[9] = (double)nref; q[10] = apr_sum; q[11] = mu_top;
         for (int r = 0; r < 4; r++) q[12 + r] = refs[r];
-        q[16] = (double)stalls; q[17] = (double)soc_fails;
+        q[16] = (double)stalls; q[17] = (double)soc_fails; q[18] = (double)boosts;
       }
       BMPC_SYNC();
       // priority list (see SCHED_LISTS)
@@ -318,6 +318,9 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
         for (int r = 0; r < 4; r++) if (r == nref) refs[r] = e0;
         nref++;
       } else if (mu < C.boost_cap) {
+        // (a solve that keeps cycling down and up the barrier ladder is not converging either: successful solves of the
+        // bench / config-4 workloads re-centre at most four times; one experiment2 instance cycled up to the iteration cap)
+        if (++boosts > C.boost_budget) { status = ST_DIVERGING; break; }
         mu = fmin(C.boost_cap, C.boost_fac * mu);
         mu_top = fmax(mu_top, mu);
         mu_changed = true;

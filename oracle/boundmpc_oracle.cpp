@@ -310,6 +310,7 @@ struct Opts {
   double boost_fac = 10, boost_cap = 1.0;   // ... -> mu <- min(cap, fac * mu)
   int max_soc = 1;            // second-order corrections per iteration
   int soc_budget = 2;         // ... until this many corrections in a row have been rejected
+  int boost_budget = 6;       // re-centrings per solve before it is stopped as locally infeasible
   int stall_stop = 3;         // third time without progress with mu at its cap: stop as locally infeasible
 };
 
@@ -613,7 +614,7 @@ struct Ipm {
     std::vector<double> xt(n), st(ni), gt(NG * N), dt_(ni);
     int status = 1;  // 0 = success, 1 = max_iter, 2 = line-search failure, 3 = regularisation failure, 5 = diverging multipliers
     int it = 0, ls_fail = 0;
-    int n_soc = 0, stalls = 0, soc_fails = 0;
+    int n_soc = 0, stalls = 0, soc_fails = 0, boosts = 0;
     std::vector<double> refs;
     for (;; it++) {
       pack_lam();
@@ -645,6 +646,9 @@ struct Ipm {
           if ((int)refs.size() >= o.red_iters) { suff = false; for (double r : refs) if (qf <= 0.9999 * r) suff = true; }
           if (suff) { if ((int)refs.size() >= o.red_iters) refs.erase(refs.begin()); refs.push_back(qf); }
           else if (mu < o.boost_cap) {
+            // (a solve that keeps cycling down and up the barrier ladder is not converging either: successful solves of the
+            // bench / config-4 workloads re-centre at most four times)
+            if (++boosts > o.boost_budget) { status = 5; break; }
             mu = std::min(o.boost_cap, o.boost_fac * mu);
             filter.clear(); refs.clear();
             if (o.verbose) printf("      no progress: mu -> %.3e\n", mu);
