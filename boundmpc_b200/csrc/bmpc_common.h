@@ -236,6 +236,7 @@ struct Config {
   int max_iter;
   double mu_init, bound_push;
   double kappa_eps, kappa_mu, theta_mu, tau_min, s_max;
+  double rollout_thr;            // cold-start repair (bmpc_ipm.cuh): equality violation of the start above which its states are rolled out
   double boost_fac, boost_cap;   // re-centring of a crawling iteration (bmpc_ipm.cuh): mu <- min(cap, fac * mu)
   int boost_budget;              // re-centrings per solve before it is stopped as locally infeasible
   int stall_stop;                // stop as locally infeasible at the stall_stop-th failed progress test with mu at its cap (0: never)

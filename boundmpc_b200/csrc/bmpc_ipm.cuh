@@ -159,6 +159,32 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   PAR_FOR(i, ne) W.y[i] = 0.0;
   BMPC_SYNC();
   eval_values(cx, C, W, p, W.x, W.c, W.d);
+  if (C.rollout_thr > 0) {
+    // Cold-start repair.  The reference's cold start (BoundMPC.py:316-321: zeros, q0, p0) used away from the start of the path
+    // has its path parameter far from where the robot is (rows violated by 0.75); Ipopt recovers from such starts in its
+    // restoration phase, this iteration does not have one.  A start whose equality rows are violated by more than
+    // rollout_thr gets its state entries replaced by the roll-out of its own inputs from the initial state (the dynamics
+    // rows are explicit, x_k = F(w_{k-1}, u_k): stage k is corrected by its residual, one evaluation per stage), kept
+    // inside the variable bounds.  Warm starts and the step-0 cold start are not touched (literal SURVEY 8d workload:
+    // 4 -> 16 of 32 cold-started instances converge, in 21 instead of 40 iterations).
+    double cv[1] = {0.0};
+    PAR_FOR(i, ne) cv[0] = fmax(cv[0], fabs(W.c[i]));
+    { const int ops[1] = {RED_MAX}; block_reduce<1>(cx, cv, ops); }
+    if (cv[0] > C.rollout_thr) {
+      for (int k = 0; k < N; k++) {
+        PAR_FOR(i, NE) {
+          const int a = 8 + i;
+          double v = W.x[NX * k + a] + W.c[NE * k + i];
+          const double l = C.lb[a], u = C.ub[a];
+          if (l > -1e300) v = fmax(v, l + C.bound_push);
+          if (u < 1e300) v = fmin(v, u - C.bound_push);
+          W.x[NX * k + a] = v;
+        }
+        BMPC_SYNC();
+        eval_values(cx, C, W, p, W.x, W.c, W.d);
+      }
+    }
+  }
   PAR_FOR(i, nd) { const double sv = fmax(-W.d[i], C.bound_push); W.s[i] = sv; W.zs[i] = mu / sv; }
   PAR_FOR(i, n) {
     const int ii = i % NX;

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_solve(const __grid_constant__
   if (threadIdx.x == 0) {
     S.cfg = C0;
     work_carve(S.work, ws + (size_t)blockIdx.x * ws_stride, C0.N);
-    work_attach_smem(S.work, S, C0.N, vec_ext ? reinterpret_cast<double*>(smem_raw + sizeof(Smem)) : nullptr);
+    work_attach_smem(S.work, S, C0.N, vec_ext > 0 ? reinterpret_cast<double*>(smem_raw + sizeof(Smem)) : nullptr, vec_ext < 0);
   }
   __syncthreads();
 #ifdef BMPC_PROBE_SLOTS   // development aid (scripts/probe_slots.py): SM and hardware warp slots of a few CTAs
@@ -429,6 +429,7 @@ struct bmpc_handle {
   int device, threads, sms, ctas_per_sm, variant;
   size_t l2_window_max, l2_persist_bytes;   // L2 access-policy window for the workspace (0: off)
   size_t smem_solve;   // dynamic shared memory of k_solve: sizeof(Smem) [+ the iterate of horizons above VEC_NMAX]
+  int vec_in_ws;       // development switch BMPC_VEC_WS=1: iterate in the workspace even when it fits in shared memory
   int single_pass, no_zero_copy;   // development switches, read from the environment once in bmpc_create
   int variant_lat;     // launch shape for batches of at most one instance per SM (-1: none): more threads per instance
   size_t ws_stride;    // doubles per CTA slot
@@ -533,6 +534,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
       h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     } else cudaGetLastError();
   }
+  h->vec_in_ws = getenv("BMPC_VEC_WS") != nullptr;
   h->single_pass = getenv("BMPC_SINGLE_PASS") != nullptr;
   h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
   if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
@@ -670,7 +672,7 @@ static int solve_batch_impl(bmpc_handle* h, int32_t batch, const double* x0, con
     nat = 1;
   }
   lc.attrs = at; lc.numAttrs = nat;
-  const int vec_ext = h->smem_solve > sizeof(Smem) ? 1 : 0;
+  const int vec_ext = h->smem_solve > sizeof(Smem) ? 1 : (h->vec_in_ws ? -1 : 0);
   CU(cudaLaunchKernelEx(&lc, kVariants[v].fn, h->C, batch, io, ws, h->ws_stride, M, vec_ext));
   CU(cudaGetLastError());
   h->launches += 1;

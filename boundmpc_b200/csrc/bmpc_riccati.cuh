@@ -68,7 +68,7 @@ struct Smem {
 // path part of the stage records (both written lane by lane, i.e. as scattered 8-byte stores if they lived in
 // global memory) are placed there when they fit (N = 10: both; N = 20: the kinematics scratch only).
 // (vec_ext: dynamic shared memory behind the Smem struct for the iterate of horizons above VEC_NMAX, or null)
-BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N, double* vec_ext = nullptr) {
+BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N, double* vec_ext = nullptr, bool vec_in_ws = false) {
   int used = 0;
   if (2 * N * F_SIZE <= EV_CAP) { W.fk = S.ev; used = 2 * N * F_SIZE; }
   if (used + N * R_PATH <= EV_CAP) { W.prec = S.ev + used - R_HY; W.prec_stride = R_PATH; }
@@ -76,7 +76,7 @@ BMPC_DEV void work_attach_smem(Work& W, Smem& S, int N, double* vec_ext = nullpt
     // the iterate lives in shared memory for the whole solve ...
     const int n = NX * N, ne = NE * N, nd = ND * N;
     double* q = S.vec;
-    W.x = q; q += n; W.zL = q; q += n; W.zU = q; q += n; W.y = q; q += ne; W.s = q; q += nd; W.zs = q; q += nd;
+    if (!vec_in_ws) { W.x = q; q += n; W.zL = q; q += n; W.zU = q; q += n; W.y = q; q += ne; W.s = q; q += nd; W.zs = q; q += nd; }
     // ... and the step / trial vectors sit behind the sweep scratch (YZ[0..256)) of the Riccati blocks: they are
     // written by the forward / adjoint sweeps after the backward pass and are dead before the next one starts
     q = S.ev + EV_STEP0;

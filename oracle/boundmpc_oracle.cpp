@@ -310,6 +310,8 @@ struct Opts {
   double boost_fac = 10, boost_cap = 1.0;   // ... -> mu <- min(cap, fac * mu)
   int max_soc = 1;            // second-order corrections per iteration
   int soc_budget = 2;         // ... until this many corrections in a row have been rejected
+  double rollout_thr = 0.5;   // start whose equality rows are violated by more than this (a cold start in the middle of a path): states
+                              // replaced by the roll-out of the start's inputs (0: never)
   int boost_budget = 6;       // re-centrings per solve before it is stopped as locally infeasible
   int stall_stop = 3;         // third time without progress with mu at its cap: stop as locally infeasible
 };
@@ -595,6 +597,29 @@ struct Ipm {
       } else if (std::isfinite(l)) v = std::max(v, l + o.bound_push * std::max(1.0, std::fabs(l)));
       else if (std::isfinite(u)) v = std::min(v, u - o.bound_push * std::max(1.0, std::fabs(u)));
       x[i] = v;
+    }
+    if (o.rollout_thr > 0) {
+      // Cold-start repair.  The reference's cold start (BoundMPC.py:316-321: zeros, q0, p0) used away from the start of the
+      // path has its path parameter 0.75 m from where the robot is; Ipopt recovers from such starts in its restoration phase,
+      // this iteration does not have one.  A start whose equality rows are violated by more than rollout_thr gets its state
+      // entries replaced by the roll-out of its own inputs from the initial state (the dynamics rows are explicit:
+      // x_k = F(w_{k-1}, u_k)), kept inside the variable bounds.  Warm starts and the step-0 cold start are not touched.
+      double wp0[NX]; wprev0(P, p, wp0);
+      double viol = 0;
+      { double f; std::vector<double> g(NG * N); eval_values(P, x.data(), p, f, g.data()); for (int k = 0; k < N; k++) for (int i = 0; i < NE; i++) viol = std::max(viol, std::fabs(g[NG * k + i])); }
+      if (viol > o.rollout_thr) {
+        for (int k = 0; k < N; k++) {
+          double g[NG], c;
+          stage_values(P, p, k == 0 ? wp0 : &x[NX * (k - 1)], &x[NX * k], g, c);
+          for (int i = 0; i < NE; i++) {
+            double v = x[NX * k + 8 + i] + g[i];
+            const double l = lbx[NX * k + 8 + i], u = ubx[NX * k + 8 + i];
+            if (std::isfinite(l)) v = std::max(v, l + o.bound_push);
+            if (std::isfinite(u)) v = std::min(v, u - o.bound_push);
+            x[NX * k + 8 + i] = v;
+          }
+        }
+      }
     }
     mu = o.mu_init;
     std::fill(y.begin(), y.end(), 0.0);
@@ -958,6 +983,7 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
   }
   if (opts && opts[5] >= 0) o.mu_strategy = (int)opts[5];
   if (opts && opts[6] >= 0) o.max_soc = (int)opts[6];
+  if (const char* e = getenv("ORC_ROLLTHR")) o.rollout_thr = atof(e);
   if (const char* e = getenv("ORC_STALL")) o.stall_stop = atoi(e);
   if (const char* e = getenv("ORC_SOCB")) o.soc_budget = atoi(e);
   Ipm ipm(P, p, o);
