@@ -242,6 +242,7 @@ struct Config {
   int stall_stop;                // stop as locally infeasible at the stall_stop-th failed progress test with mu at its cap (0: never)
   int soc_budget;                // corrections rejected in a row after which none is tried any more in a solve
   int max_soc;                   // second-order corrections per iteration (0 or 1)
+  int qss_late;                  // Riccati stage: Q_ss pass in the gain phase (idle warps) instead of the Q_u phase
   int hard_continue;             // != 0: instances flagged hard at the end of their slice continue instead of being parked
   int slice_iters;               // iterations of pass A of the two-pass scheduling (bmpc_ipm.cuh)
   int red_iters;                 // ... when the optimality error has not improved on any of the last red_iters iterates (<= 4)

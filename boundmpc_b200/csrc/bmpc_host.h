@@ -45,6 +45,7 @@ inline int make_config(const bmpc_config& in, Config& C) {
   // 27 instead of 42 iterations per infeasible instance; the bench workload loses no converging instance).
   C.stall_stop = 3; C.boost_budget = 6;
   C.rollout_thr = 0.5;
+  C.qss_late = 0;     // (Q_ss pass on the idle warps of the gain phase: 57.9 vs 55.4 ms, the two warps then outlast the Cholesky chains)
   C.slice_iters = 6; C.hard_continue = 0;   // (continuing hard instances instead of parking them: 55.1 vs 54.9 ms on shard 4, no gain)
   // One second-order correction per iteration (Ipopt: max_soc = 4; on the bench workload a second correction is never
   // accepted when the first is not): 0.9 % extra KKT solves, 7 % fewer iterations along the experiment1 closed loop.

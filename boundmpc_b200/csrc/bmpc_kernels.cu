@@ -539,6 +539,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
   h->no_zero_copy = getenv("BMPC_NO_ZERO_COPY") != nullptr;
   if (const char* e_ = getenv("BMPC_SLICE_ITERS")) { const int v_ = atoi(e_); if (v_ >= 1) h->C.slice_iters = v_; }
   if (const char* e_ = getenv("BMPC_MAX_SOC")) h->C.max_soc = atoi(e_) > 0 ? 1 : 0;
+  if (const char* e_ = getenv("BMPC_QSS_LATE")) h->C.qss_late = atoi(e_) > 0 ? 1 : 0;
   if (const char* e_ = getenv("BMPC_HARD_CONTINUE")) h->C.hard_continue = atoi(e_) > 0 ? 1 : 0;
   h->dbuf = nullptr; h->dbuf_bytes = 0;
   h->pin = nullptr; h->pin_bytes = 0;

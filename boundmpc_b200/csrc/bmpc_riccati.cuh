@@ -460,10 +460,12 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
       S.qv[a] = v;
     }
   }
-  if (!first) {   // (S.M is dead: phase 3 reads Q_uu's M block from S.Muu)
+  // Q_ss pass (S.M is dead: phase 3 reads Q_uu's M block from S.Muu).  It needs Y only and is needed by phase 5 only, so it
+  // can run in phase 3 on all warps or (C.qss_late) in phase 4 on the warps that have no gain column to solve.
+  auto qss_pass = [&](int w0, int w1) {
   // Q_ss, integrator rows of G^T Y: item (j, b) -> rows um_j, q_j, dq_j, ddq_j of column b; O-terms:
   // rows v_{k+1} x cols v_k carry ovv, row ddphi_{k+1} carries odv (E^T O [I 0] + transpose)
-  PAR_FOR(it, 8 * NX) {
+  ROLE_FOR(it, 8 * NX, w0, w1) {
     const int j = it / NX, b = it - NX * j;
     const TrivOut o = triv_combine(C, S.YZ[(8 + trow(j, 0)) * LDY + b], S.YZ[(8 + trow(j, 1)) * LDY + b], S.YZ[(8 + trow(j, 2)) * LDY + b]);
     double vv[4] = {o.um, o.q, o.dq, o.ddq};
@@ -481,7 +483,7 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
   // rows p_pos, p_rot, v: no integrator part.  Phase 5 reads Q_ss only through the upper tiles (tile row <= tile
   // column) and writes P_k symmetrically, so of these 12 rows only the columns from the first column of their tile
   // row on are needed: 3 x 20 + 8 x 12 + 4 = 160 entries instead of 528.
-  PAR_FOR(it, 160) {
+  ROLE_FOR(it, 160, w0, w1) {
     int a, b;
     if (it < 60) { a = 29 + it / 20; b = 24 + it - 20 * (it / 20); }
     else if (it < 156) { const int q = it - 60; a = 32 + q / 12; b = 32 + q - 12 * (q / 12); }
@@ -494,7 +496,9 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
     }
     S.M[a * LDM + b] = v;
   }
-  }
+  };
+  const bool qss_late = C.qss_late && nw > 2;
+  if (!first && !qss_late) qss_pass(0, nw);
   BMPC_SYNC();
   BMPC_TMARK(11);
   // ---- phase 4, warps 0-1: gains K = -Q_uu^{-1} Q_us (8 x 44), kappa = -Q_uu^{-1} q_u (one column per
@@ -519,6 +523,7 @@ BMPC_DEV bool riccati_stage(const Ctx cx, const Config& C, const Work& W, const 
   if (!first) {
     if (in_role(cx, 2, nw)) stage_prefetch(cx, C, W, S, k - 1, 2, nw);   // asynchronous, completed below
     BMPC_TMARK2(49);
+    if (qss_late) qss_pass(2, nw);
     cp_async_wait();
     BMPC_TMARK2(52);
   }

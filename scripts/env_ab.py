@@ -20,6 +20,7 @@ for sp in specs:
     for k, v in old.items():
         if v is None: os.environ.pop(k, None)
         else: os.environ[k] = v
+ref = None
 for rnd in range(2):
     for sp, s in zip(specs, solvers):
         out = s.solve_batch(xd, pd); torch.cuda.synchronize()
@@ -29,4 +30,7 @@ for rnd in range(2):
             e0.record(); s.solve_batch(xd, pd, out); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         it = out["iters"]
-        print(f"round {rnd} {sp:40s} {best:.2f} ms  {B / best * 1e3:.0f} solves/s  iters mean {it.double().mean():.3f} max {int(it.max())} ok {int((out['status'] == 0).sum())}", flush=True)
+        xh = out["x"].cpu().numpy()
+        if ref is None: ref = xh
+        same = bool(np.array_equal(xh, ref))
+        print(f"round {rnd} {sp:40s} {best:.2f} ms  {B / best * 1e3:.0f} solves/s  iters mean {it.double().mean():.3f} max {int(it.max())} ok {int((out['status'] == 0).sum())} bitwise same as first: {same}", flush=True)
