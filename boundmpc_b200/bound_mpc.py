@@ -11,6 +11,13 @@ Reference behaviour kept on purpose: row `nr_segs` of the bound-
 tables is never written by the reference (np.empty) — it is zero here, the solver never selects
 it arithmetically; `weights[4]` doubles as dphi_max; only the first entry of e_p_min / e_r_min /
 e_p_max / e_r_max / s is used; `updated` is never reset after `update()`.
+
+Known deviation of the mirror: `prev_traj / prev_vel / prev_acc / prev_jerk` — the inputs of the re-projected
+warm start after `update()` — come from the solver's own columns of `w_opt`; in the reference they are views that end up
+holding the re-integrated trajectory for the columns >= error_count.  The two agree to solver tolerance when
+error_count == 0 and differ after a fallback step followed by `update()`; the device path (`k_prepare`) follows the
+mirror.  tests/test_replan.py covers update() with and without preceding fallback steps against the mirror, not against
+the reference, for that combination.
 """
 import copy
 import time

@@ -47,8 +47,8 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 // iterations: optimality error grown over the slice, barrier parameter raised, or steps cut to a crawl), the others by
 // the size of the optimality error at the slice boundary, which predicts the remaining iterations to +-2 (bench
 // workload: e0 >= 0.1: 6-8 to go, >= 1e-4: ~4, below: 1-2).  A plain work queue leaves 30 % of the GPU idle behind the
-// long solves; two lists (hard / normal) still 8 % behind the ordinary 15-iteration ones picked up last.  Results do not
-// depend on where an instance is parked.
+// long solves; with these lists 443-444 of the 444 CTA slots stay busy until the last millisecond of a launch
+// (scripts/trace_util.py).  Results do not depend on where an instance is parked.
 constexpr int SCHED_LISTS = 4;
 constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls, soc_fails, boosts)
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
