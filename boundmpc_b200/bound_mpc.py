@@ -129,7 +129,13 @@ class BoundMPC:
         self.prev_infeasible_solution = None
         self.lam_g0 = 0
         self.lam_x0 = 0
-        self.solver_opts = solver_opts if solver_opts is not None else {}
+        # (the reference builds this dictionary itself, BoundMPC.py:120-148; the handle reads tol and max_iter from it, the
+        # other entries describe Ipopt's strategy, which csrc/bmpc_ipm.cuh restates)
+        self.solver_opts = solver_opts if solver_opts is not None else {
+            'verbose': False, 'verbose_init': False, 'print_time': False,
+            'ipopt': {'tol': 10e-6, 'max_iter': 500, 'mu_strategy': 'adaptive', 'adaptive_mu_globalization': 'kkt-error',
+                      'warm_start_init_point': 'yes', 'mu_oracle': 'loqo', 'line_search_method': 'filter',
+                      'expect_infeasible_problem': 'no', 'print_level': 0}}
         if solver is not None:      # share one CUDA handle between many controller objects
             self.solver = solver
             lbx, ubx, lbg, ubg = solver.bounds()

@@ -30,8 +30,8 @@ import numpy as np, torch
 from boundmpc_b200.ocp import default_solver
 from boundmpc_b200 import batches
 B, outp = int(sys.argv[2]), sys.argv[3]
-s = default_solver()
-x0, p = batches.make_batch(s, ("exp1", "exp2"), int(os.environ.get("AB_FIRST", "0")), B, bound_scale=True)
+s = default_solver(solver_opts={'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}})
+x0, p = batches.make_batch(default_solver(), ("exp1", "exp2"), int(os.environ.get("AB_FIRST", "0")), B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 out = s.solve_batch(xd, pd); torch.cuda.synchronize()
 best = 1e9

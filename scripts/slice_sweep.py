@@ -6,13 +6,13 @@ from boundmpc_b200.ocp import default_solver
 from boundmpc_b200 import batches
 B = 8192
 shard = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-s0 = default_solver()
-x0, p = batches.make_batch(s0, ("exp1", "exp2"), shard * B, B, bound_scale=True)
+s0 = default_solver(solver_opts={'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}})
+x0, p = batches.make_batch(default_solver(), ("exp1", "exp2"), shard * B, B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 ref = None
 for k in [int(a) for a in sys.argv[2:]] or [3, 4, 5, 6, 7, 8]:
     os.environ["BMPC_SLICE_ITERS"] = str(k)
-    s = default_solver()
+    s = default_solver(solver_opts={'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}})
     out = s.solve_batch(xd, pd); torch.cuda.synchronize()
     best = 1e9
     for rep in range(4):

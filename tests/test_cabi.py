@@ -37,3 +37,16 @@ def test_fails_loudly_without_gpu():
     from boundmpc_b200.ocp import default_solver
     with pytest.raises(_cabi.BmpcError):
         default_solver()
+
+
+def test_tolerance_option_resolution():
+    """`ipopt.tol` is honoured as the reference's Ipopt honours it (BoundMPC.py:121), `b200.tol` overrides, default 1e-9;
+    a controller that builds its own solver passes the reference's option dictionary."""
+    from boundmpc_b200.ocp import resolve_tol
+    assert resolve_tol(None) == 1e-9 and resolve_tol({}) == 1e-9
+    assert resolve_tol({"ipopt": {"tol": 10e-6, "max_iter": 500}}) == 1e-5
+    assert resolve_tol({"ipopt": {"tol": 10e-6}, "b200": {"tol": 1e-8}}) == 1e-8
+    assert resolve_tol({"b200": {"threads": 384}}) == 1e-9
+    import inspect
+    from boundmpc_b200 import bound_mpc
+    assert "'tol': 10e-6" in inspect.getsource(bound_mpc.BoundMPC.__init__)
