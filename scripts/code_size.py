@@ -6,7 +6,7 @@ tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(lib)} >/dev/null 2>&1", shell=True)
 cub = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
 dis = subprocess.run(f"nvdisasm -g -c {tmp}/{cub}", shell=True, capture_output=True, text=True).stdout.splitlines()
-root = os.path.join(os.path.dirname(os.path.abspath(lib)), 'csrc')
+root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'boundmpc_b200', 'csrc')
 funcs = {}
 for f in os.listdir(root):
     starts = []

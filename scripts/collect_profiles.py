@@ -15,7 +15,7 @@ for a, b in [("bench.json", "bench.json"), ("bench_reference.json", "bench_refer
     cp(a, b)
 for cfg in ("exp1_1024", "exp2_8192", "exp1_N20_tight_8192", "spec_mixed_65536"):
     cp(f"bench_{cfg}.json", f"bench_{cfg}.json")
-hdr = "# ncu --set full --clock-control none of ONE k_solve launch (8,192 instances, 1 B200), round 2 final code; numbers under the profiler are not bench values\n"
+hdr = "# ncu --set full --clock-control none of ONE k_solve launch (8,192 instances, 1 B200, tol = AB_TOL of scripts/profile_batch.py: 1e-5 from r2b on), final code of the round; numbers under the profiler are not bench values\n"
 for raw, out, what in [("prof_raw.csv", "k_solve_metrics.txt", "mixed_65536 shard"), ("prof_n20_raw.csv", "k_solve_N20_metrics.txt", "exp1_N20_tight_8192")]:
     f = os.path.join(src, raw)
     if os.path.exists(f):
@@ -28,15 +28,15 @@ if os.path.exists(f):
     open(os.path.join(P, f"{pre}_k_solve_by_function.txt"), "w").write("# warp-state samples of k_solve<128,3> by source function (ncu source page joined with nvdisasm line info)\n" + txt.stdout + txt.stderr[-500:])
     print("wrote by_function")
 tr = {}
-for w, name in ((0, "with_l2_window"), (1, "without_l2_window")):
-    f = os.path.join(src, f"dram_nowindow{w}.csv")
+for w, name in ((0, "with_l2_window"), (1, "without_l2_window"), (2, "default")):
+    f = os.path.join(src, f"dram_nowindow{w}.csv" if w < 2 else "dram.csv")
     if os.path.exists(f):
         rows = [r for r in csv.reader(open(f)) if len(r) > 5]
         h = rows[0]
         iN, iV = h.index("Metric Name"), h.index("Metric Value")
         tr[name] = {r[iN]: float(r[iV].replace(",", "")) for r in rows[1:] if "k_solve" in " ".join(r)}
 if tr:
-    d = tr.get("with_l2_window", {})
+    d = tr.get("default") or tr.get("with_l2_window", {})
     tot = None
     if d:
         rd, wr = d.get("dram__bytes_read.sum", 0), d.get("dram__bytes_write.sum", 0)

@@ -14,8 +14,9 @@ NAMES = {0: "full: integrate+sincos", 1: "full: path<1> | fk -> kin residual, cu
          19: "ls: trial point", 20: "ls: merit reduce", 21: "accept step", 22: "init point", 23: "report", 30: "  riccati 5: dmma tiles (warp 0)", 31: "  riccati 5: pv", 35: "  full: path blocks", 36: "  full: grad f", 40: "  riccati 5: flag check", 42: "  riccati 4: factorisation + solves (thread 0)", 48: "  [thread 64] up to phase 4", 49: "  [thread 64] riccati 4: prefetch issue", 50: "  [thread 64] riccati 4: Qss pass 1", 51: "  [thread 64] riccati 4: Qss pass 2", 52: "  [thread 64] riccati 4: cp.async wait", 44: "  [thread 64] everything up to phase 5", 45: "  [thread 64] riccati 5 tiles",
          46: "  [thread 64] riccati 5 pv", 47: "  [thread 64] riccati 5 end barrier"}
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-s = default_solver()
-x0, p = batches.make_batch(s, ("exp1", "exp2"), 0, B, bound_scale=True)
+gen = default_solver()   # the workload is drawn from the tight closed loops whatever the measured tolerance is
+s = default_solver(solver_opts={'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}})
+x0, p = batches.make_batch(gen, ("exp1", "exp2"), 0, B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 out = s.solve_batch(xd, pd); torch.cuda.synchronize()
 L = _cabi.lib()

@@ -9,8 +9,9 @@ from boundmpc_b200 import batches
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 name = sys.argv[2] if len(sys.argv) > 2 else "mixed_65536"
 c = dict(batches.CONFIGS[name]); c.pop("count"); n = c.pop("n")
-s = default_solver(N=n)
-x0, p = batches.make_batch(s, first=0, count=B, n=n, **c)
+gen = default_solver(N=n)
+s = default_solver(N=n, solver_opts={'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}})
+x0, p = batches.make_batch(gen, first=0, count=B, n=n, **c)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 out = s.solve_batch(xd, pd); torch.cuda.synchronize()
 torch.cuda.profiler.start()
