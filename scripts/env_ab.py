@@ -9,6 +9,7 @@ B = 8192
 shard = int(sys.argv[1])
 specs = sys.argv[2:] or ["BMPC_MAX_SOC=1", "BMPC_MAX_SOC=0"]
 s0 = default_solver()
+TOL = {'b200': {'tol': float(os.environ.get('AB_TOL', '1e-5'))}}
 x0, p = batches.make_batch(s0, ("exp1", "exp2"), shard * B, B, bound_scale=True)
 xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
 solvers = []
@@ -16,7 +17,7 @@ for sp in specs:
     kv = dict(a.split("=") for a in sp.split(",") if a)
     old = {k: os.environ.get(k) for k in kv}
     os.environ.update(kv)
-    solvers.append(default_solver())
+    solvers.append(default_solver(solver_opts=TOL))
     for k, v in old.items():
         if v is None: os.environ.pop(k, None)
         else: os.environ[k] = v
