@@ -43,13 +43,16 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 
 // Two-pass scheduling of a batch (k_solve): pass A runs the first C.slice_iters iterations of every instance and
 // parks the iterate in global memory; pass B resumes the parked instances in the order of the work they have left
-// (longest-processing-time-first): SCHED_LISTS priority lists, list 0 = "hard" (the few instances that go on for 20-50
-// iterations: optimality error grown over the slice, barrier parameter raised, or steps cut to a crawl), the others by
-// the size of the optimality error at the slice boundary, which predicts the remaining iterations to +-2 (bench
-// workload: e0 >= 0.1: 6-8 to go, >= 1e-4: ~4, below: 1-2).  A plain work queue leaves 30 % of the GPU idle behind the
+// (longest-processing-time-first): SCHED_LISTS priority lists.  List 1 = "hard" (optimality error grown over the slice,
+// barrier parameter raised, or steps cut to a crawl: 15 % of the bench workload after a four-iteration slice, 5 - 17
+// iterations to go); list 0 = the hard instances whose optimality error is still above 20 after steps cut below 0.25
+// on average (5.6 % of the batch: one wave of resident CTAs; every solve of the 65,536-instance workload that goes on
+// for 30 - 54 iterations is among them, and one of those resumed a wave late stretches its launch by 8 %); the
+// others by the size of the optimality error at the slice boundary, which predicts the remaining iterations to +-2
+// (e0 >= 0.1: 6-8 to go, >= 1e-4: ~4, below: 1-2).  A plain work queue leaves 30 % of the GPU idle behind the
 // long solves; with these lists 443-444 of the 444 CTA slots stay busy until the last millisecond of a launch
 // (scripts/trace_util.py).  Results do not depend on where an instance is parked.
-constexpr int SCHED_LISTS = 4;
+constexpr int SCHED_LISTS = 5;
 constexpr int SAVE_FILT = 128, SAVE_SCAL = 24;   // (scalars: 9 loop variables, nref, apr_sum, mu_top, refs[4], stalls, soc_fails, boosts)
 BMPC_HD size_t save_doubles(int N) { return (size_t)3 * NX * N + (size_t)NE * N + (size_t)2 * ND * N + SAVE_FILT + SAVE_SCAL; }
 enum { RUN_FULL = 0, RUN_SLICE = 1, RUN_RESUME = 2 };            // mode of solve_instance
@@ -228,8 +231,8 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
       }
       BMPC_SYNC();
       // priority list (see SCHED_LISTS)
-      if (hard) return PARKED + 0;
-      return PARKED + (kkt_final >= 0.1 ? 1 : (kkt_final >= 1e-4 ? 2 : 3));
+      if (hard) return PARKED + ((kkt_final >= 20.0 && apr_sum < 0.25 * it) ? 0 : 1);
+      return PARKED + (kkt_final >= 0.1 ? 2 : (kkt_final >= 1e-4 ? 3 : 4));
     }
     eval_full(cx, C, W, p, W.x);
     // ---- optimality error (Ipopt's E_mu), constraint violation theta
