@@ -77,3 +77,37 @@ def test_bench_batch_sample_against_oracle():
             assert active_set({"x": r["x"][j], "g": r["g"][j]}) == active_set(ro)
             assert abs(int(r["iters"][j]) - ro["iters"]) <= 2
     assert same >= len(idx) - 2
+
+
+def test_bench_size_batch_at_reference_tolerance():
+    """The 8,192-instance bench shard with the reference's own `ipopt.tol` (BoundMPC.py:121), the setting bench.py reports:
+    same termination status per instance as the tight solve, Ipopt's scaled error <= 1e-5, feasible in the reference's own
+    sense (BoundMPC.py:461-465), never more iterations than the tight solve, joint trajectories within 2e-3 of the tight
+    ones (median 1e-5); every 128th instance against the oracle at the same tolerance (status, iterations, solution)."""
+    from boundmpc_b200 import batches
+    from boundmpc_b200.ocp import default_solver
+    from oracle import oracle as O
+    tight = _solver(10)
+    ref = default_solver(N=10, nr_segs=4, dt=0.1, solver_opts={"ipopt": {"tol": 10e-6, "max_iter": 500}})
+    B = 8192
+    x0, p = batches.make_batch(tight, ("exp1", "exp2"), 0, B, bound_scale=True)
+    xd, pd = torch.from_numpy(x0).cuda(), torch.from_numpy(p).cuda()
+    a = {k: v.cpu().numpy() for k, v in tight.solve_batch(xd, pd).items()}
+    b = {k: v.cpu().numpy() for k, v in ref.solve_batch(xd, pd).items()}
+    assert np.array_equal(a["status"], b["status"])
+    ok = b["status"] == 0
+    assert ok.mean() >= 0.999 and b["kkt"][ok].max() <= 1e-5
+    assert (b["iters"][ok] <= a["iters"][ok]).all() and b["iters"].mean() < 0.8 * a["iters"].mean()
+    g = b["g"][ok].reshape(-1, 10, 43)
+    viol = np.abs(g[:, :, :36]).clip(1e-6, None).sum(axis=(1, 2)) - 360e-6 + g[:, :, 36:].clip(1e-6, None).sum(axis=(1, 2)) - 70e-6
+    assert viol.max() < 1e-4
+    qa, qb = a["x"][ok].reshape(-1, 10, 44)[:, :, 8:15], b["x"][ok].reshape(-1, 10, 44)[:, :, 8:15]
+    rel = np.abs(qa - qb).max(axis=(1, 2)) / np.abs(qa).max(axis=(1, 2))
+    assert rel.max() < 2e-3 and np.median(rel) < 5e-5
+    for i in range(0, B, 128):
+        ro = O.solve(x0[i], p[i], tol=1e-5)
+        assert ro["status"] == b["status"][i]
+        if ro["status"] == 0:
+            assert abs(int(b["iters"][i]) - ro["iters"]) <= 1
+            if int(b["iters"][i]) == ro["iters"]:
+                assert np.abs(ro["x"] - b["x"][i]).max() < 1e-5
