@@ -313,7 +313,6 @@ struct Opts {
   double rollout_thr = 0.5;   // start whose equality rows are violated by more than this (a cold start in the middle of a path): states
                               // replaced by the roll-out of the start's inputs (0: never)
   int boost_budget = 6;       // re-centrings per solve before it is stopped as locally infeasible
-  int y_full = 0; double slack_push = 0; double y_init_ls = 0;
   int stall_stop = 3;         // third time without progress with mu at its cap: stop as locally infeasible
 };
 
@@ -628,7 +627,7 @@ struct Ipm {
       double f;
       std::vector<double> g(NG * N), d(ND * N);
       eval_values(P, x.data(), p, f, g.data(), d.data());
-      for (int i = 0; i < ni; i++) s[i] = std::max(-d[i], o.slack_push > 0 ? o.slack_push : o.bound_push);
+      for (int i = 0; i < ni; i++) s[i] = std::max(-d[i], o.bound_push);
     }
     for (int i = 0; i < ni; i++) zs[i] = mu / s[i];
     for (int i = 0; i < n; i++) {
@@ -844,8 +843,7 @@ struct Ipm {
       if (trace && it < trace_cap) { double* T = trace + 6 * it; T[0] = e0; T[1] = mu; T[2] = apr; T[3] = alpha; T[4] = th_cur; T[5] = dw; }
       for (int i = 0; i < n; i++) x[i] += alpha * dx[i];
       for (int i = 0; i < ni; i++) s[i] += alpha * ds[i];
-      { const double ay = o.y_full == 1 ? 1.0 : (o.y_full == 2 ? std::max(alpha, adu) : (o.y_full == 3 ? (it == 0 ? 1.0 : alpha) : alpha));
-        for (int i = 0; i < ne; i++) y[i] += ay * (ynew[i] - y[i]); }
+      for (int i = 0; i < ne; i++) y[i] += alpha * (ynew[i] - y[i]);
       const double ks = 1e10;
       for (int i = 0; i < ni; i++) {
         zs[i] += adu * dzs[i];
@@ -988,9 +986,6 @@ int orc_solve(int N, int S, double dt, const double* x0, const double* p, const 
   if (const char* e = getenv("ORC_ROLLTHR")) o.rollout_thr = atof(e);
   if (const char* e = getenv("ORC_STALL")) o.stall_stop = atoi(e);
   if (const char* e = getenv("ORC_SOCB")) o.soc_budget = atoi(e);
-  if (const char* e = getenv("ORC_YFULL")) o.y_full = atoi(e);
-  if (const char* e = getenv("ORC_SPUSH")) o.slack_push = atof(e);
-  if (const char* e = getenv("ORC_TAUMIN")) o.tau_min = atof(e);
   Ipm ipm(P, p, o);
   ipm.trace = g_trace; ipm.trace_cap = g_trace_cap;
   int it = 0;
