@@ -50,7 +50,7 @@ inline int make_config(const bmpc_config& in, Config& C) {
   // profiles/r2b_shard_slice.json: 42.1 ... 43.5 ms at tol 1e-5 against 42.9 ... 48.4 ms with six, the same within noise at tol
   // 1e-9; a solve at the reference's tolerance takes 7.4 iterations on average, so a six-iteration slice parks most
   // instances one iteration before their end).
-  C.slice_iters = 4; C.hard_continue = 0;   // (continuing hard instances instead of parking them: 55.1 vs 54.9 ms on shard 4, no gain)
+  C.slice_iters = 4; C.hard_continue = 0;   // (continuing hard instances instead of parking them: slower on every shard measured)
   // One second-order correction per iteration (Ipopt: max_soc = 4; on the bench workload a second correction is never
   // accepted when the first is not): 0.9 % extra KKT solves, 7 % fewer iterations along the experiment1 closed loop.
   C.max_soc = 1; C.soc_budget = 2;

@@ -205,9 +205,8 @@ BMPC_DEV int solve_instance(const Ctx cx, const Config& C, const Work& W, Smem& 
   const double nzcnt = (double)N * (ND + nbnd);
 
   for (;; it++) {
-    // "hard" (see SCHED_LISTS): on the bench workload these tests flag 6 % of the batch and every instance with more than
-    // 22 iterations to go.  With C.hard_continue a hard instance is not parked at all but goes on at once (measured: no gain
-    // over resuming it first in pass B, a solve picked up late in pass A is the tail either way; off by default).
+    // "hard" (see SCHED_LISTS).  With C.hard_continue a hard instance is not parked at all but goes on at once (measured:
+    // slower than resuming it first in pass B on every shard; a solve picked up late in pass A is the tail either way).
     const bool slice_end = mode == RUN_SLICE && it == C.slice_iters;
     const bool hard = slice_end && (kkt_final > e0_first || mu_top > C.mu_init || apr_sum < 0.3 * it);
     if (slice_end && hard && C.hard_continue) mode = RUN_FULL;
