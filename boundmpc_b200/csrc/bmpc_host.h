@@ -46,11 +46,12 @@ inline int make_config(const bmpc_config& in, Config& C) {
   C.stall_stop = 3; C.boost_budget = 6;
   C.rollout_thr = 0.5;
   C.qss_late = 0;     // (Q_ss pass on the idle warps of the gain phase: 57.9 vs 55.4 ms, the two warps then outlast the Cholesky chains)
-  // Pass A of the two-pass scheduling runs four iterations (all eight shards of the 65,536-instance workload, one GPU,
-  // profiles/r2b_shard_slice.json: 42.1 ... 43.5 ms at tol 1e-5 against 42.9 ... 48.4 ms with six, the same within noise at tol
-  // 1e-9; a solve at the reference's tolerance takes 7.4 iterations on average, so a six-iteration slice parks most
-  // instances one iteration before their end).
-  C.slice_iters = 4; C.hard_continue = 0;   // (continuing hard instances instead of parking them: slower on every shard measured)
+  // Pass A of the two-pass scheduling runs three iterations (was six).  A solve at the reference's tolerance takes 7.4
+  // iterations on average, so a six-iteration slice parks most instances one iteration before their end.  All eight shards
+  // of the 65,536-instance workload on one GPU at tol 1e-5: 42.9 ... 48.4 ms with six, 42.1 ... 43.5 with four
+  // (profiles/r2b_shard_slice.json, four priority lists); with the fifth list 41.7 ... 43.1 ms with three against 42.1 ...
+  // 44.0 with four (r2b_shard_slice_5lists.json); at tol 1e-9 all of them within noise (55.3 ... 56.2 ms).
+  C.slice_iters = 3; C.hard_continue = 0;   // (continuing hard instances instead of parking them: slower on every shard measured)
   // One second-order correction per iteration (Ipopt: max_soc = 4; on the bench workload a second correction is never
   // accepted when the first is not): 0.9 % extra KKT solves, 7 % fewer iterations along the experiment1 closed loop.
   C.max_soc = 1; C.soc_budget = 2;

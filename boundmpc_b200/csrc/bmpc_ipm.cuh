@@ -44,10 +44,11 @@ BMPC_DEV bool is_fin(double v) { return v > -1e300 && v < 1e300; }
 // Two-pass scheduling of a batch (k_solve): pass A runs the first C.slice_iters iterations of every instance and
 // parks the iterate in global memory; pass B resumes the parked instances in the order of the work they have left
 // (longest-processing-time-first): SCHED_LISTS priority lists.  List 1 = "hard" (optimality error grown over the slice,
-// barrier parameter raised, or steps cut to a crawl: 15 % of the bench workload after a four-iteration slice, 5 - 17
+// barrier parameter raised, or steps cut to a crawl: a quarter of the bench workload after a three-iteration slice, 5 - 18
 // iterations to go); list 0 = the hard instances whose optimality error is still above 20 after steps cut below 0.25
-// on average (5.6 % of the batch: one wave of resident CTAs; every solve of the 65,536-instance workload that goes on
-// for 30 - 54 iterations is among them, and one of those resumed a wave late stretches its launch by 8 %); the
+// on average (11 % of the batch after three iterations, 5.6 % after four; every solve of the 65,536-instance workload
+// that goes on for 30 - 54 iterations is among them, and one of those resumed behind 1,200 other hard instances
+// stretched its launch by 8 %); the
 // others by the size of the optimality error at the slice boundary, which predicts the remaining iterations to +-2
 // (e0 >= 0.1: 6-8 to go, >= 1e-4: ~4, below: 1-2).  A plain work queue leaves 30 % of the GPU idle behind the
 // long solves; with these lists 443-444 of the 444 CTA slots stay busy until the last millisecond of a launch
