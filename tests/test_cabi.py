@@ -50,3 +50,16 @@ def test_tolerance_option_resolution():
     import inspect
     from boundmpc_b200 import bound_mpc
     assert "'tol': 10e-6" in inspect.getsource(bound_mpc.BoundMPC.__init__)
+
+
+def test_initial_multipliers_are_reported_as_ignored():
+    """`solver(..., lam_g0=, lam_x0=)` keeps CasADi's signature; non-zero initial multipliers are not used and say so once."""
+    import warnings
+    import numpy as np
+    from boundmpc_b200 import ocp
+    ocp._DUAL_NOTE[0] = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert not ocp.note_dual_start(None, None) and not ocp.note_dual_start(0, np.zeros(4))     # the reference's initial values (BoundMPC.py:114-116)
+        assert ocp.note_dual_start(np.ones(3), None) and ocp.note_dual_start(np.ones(3), None)
+    assert len([x for x in w if "lam_g0" in str(x.message)]) == 1
